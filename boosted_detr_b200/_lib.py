@@ -1,0 +1,99 @@
+"""ctypes binding of libbdetr.so (include/bdetr.h).  There is NO fallback: if the CUDA library is
+missing or a call fails, the product path raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_float, c_int, c_int32, c_longlong, c_size_t, c_uint32, c_void_p, c_char_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbdetr.so")
+
+BDETR_OK = 0
+BDETR_E_BAD_SHAPE, BDETR_E_CUDA, BDETR_E_INVALID_COST, BDETR_E_INFEASIBLE, BDETR_E_NULL, BDETR_E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
+MODE_FP32, MODE_BF16 = 0, 1
+
+
+class BdetrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libbdetr status {code}: {msg}")
+        self.code = code
+
+
+def _ptr_struct(name, fields):
+    return type(name, (Structure,), {"_fields_": [(f, c_void_p) for f in fields]})
+
+
+AttnParams = _ptr_struct("AttnParams", ["wq", "bq", "wk", "bk", "wv", "bv", "wo", "bo", "ln_gamma", "ln_beta"])
+AttnSaved = _ptr_struct("AttnSaved", ["qp", "kp", "vp", "o", "lse", "z", "mean", "rstd"])
+AttnScratch = _ptr_struct("AttnScratch", ["d_qp", "d_kp", "d_vp", "d_o", "d_z", "delta"])
+FfnParams = _ptr_struct("FfnParams", ["w1", "b1", "w2", "b2", "ln_gamma", "ln_beta"])
+FfnSaved = _ptr_struct("FfnSaved", ["h", "z", "mean", "rstd"])
+FfnScratch = _ptr_struct("FfnScratch", ["d_z", "d_h"])
+HeadParams = _ptr_struct("HeadParams", ["w1", "b1", "bn_gamma", "bn_beta", "bn_moving_mean", "bn_moving_var", "w2", "b2"])
+HeadSaved = _ptr_struct("HeadSaved", ["h", "hn", "bn_mean", "bn_rstd", "act"])
+HeadScratch = _ptr_struct("HeadScratch", ["d_logits", "d_hn", "d_h"])
+
+P = c_void_p
+I = c_int
+F = c_float
+
+# name -> (restype, argtypes); must list every function declared in include/bdetr.h
+PROTOTYPES = {
+    "bdetr_version": (c_int, []),
+    "bdetr_last_error": (c_char_p, []),
+    "bdetr_set_mode": (c_int, [I]),
+    "bdetr_get_mode": (c_int, []),
+    "bdetr_launch_count": (c_longlong, []),
+    "bdetr_reset_launch_count": (None, []),
+    "bdetr_cost_matrix_fwd": (c_int, [I, I, I, I, I, P, P, P, P, P, P, F, F, F, P, P]),
+    "bdetr_lsap_assign": (c_int, [I, I, I, P, P, P, P, P, P, P, P]),
+    "bdetr_lsap_smem_bytes": (c_size_t, [I, I]),
+    "bdetr_matched_loss_fwd": (c_int, [I, I, I, I, I, P, P, P, P, P, P, P, P, P, F, F, F, F, P, P, P]),
+    "bdetr_matched_loss_bwd": (c_int, [I, I, I, I, I, P, P, P, P, P, P, P, P, P, F, F, F, F, F, P, P, P, P]),
+    "bdetr_attention_block_fwd": (c_int, [I, I, I, I, I, P, P, P, POINTER(AttnParams), F, c_uint32, F, P,
+                                          POINTER(AttnSaved), P]),
+    "bdetr_attention_block_bwd": (c_int, [I, I, I, I, I, P, P, P, POINTER(AttnParams), F, c_uint32,
+                                          POINTER(AttnSaved), P, P, P, P, I, POINTER(AttnParams),
+                                          POINTER(AttnScratch), P]),
+    "bdetr_ffn_block_fwd": (c_int, [I, I, P, POINTER(FfnParams), F, c_uint32, F, P, POINTER(FfnSaved), P]),
+    "bdetr_ffn_block_bwd": (c_int, [I, I, P, POINTER(FfnParams), F, c_uint32, POINTER(FfnSaved), P, P, I,
+                                    POINTER(FfnParams), POINTER(FfnScratch), P]),
+    "bdetr_add_positional_fwd": (c_int, [I, I, I, P, P, P, P]),
+    "bdetr_add_positional_bwd": (c_int, [I, I, I, P, P, P]),
+    "bdetr_tile_queries_fwd": (c_int, [I, I, I, P, P, P]),
+    "bdetr_accumulate": (c_int, [c_size_t, P, P, P]),
+    "bdetr_head_fwd": (c_int, [I, I, I, I, I, I, F, P, POINTER(HeadParams), F, F, P, I, POINTER(HeadSaved), P]),
+    "bdetr_head_bwd": (c_int, [I, I, I, I, I, F, P, POINTER(HeadParams), F, POINTER(HeadSaved), P, P, I,
+                               POINTER(HeadParams), POINTER(HeadScratch), P]),
+    "bdetr_gemm": (c_int, [I, I, I, P, I, P, I, P, I, I, P, P]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Loads libbdetr.so (built by boosted_detr_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -m boosted_detr_b200.build` (or __graft_entry__.build()). "
+            "There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != BDETR_OK:
+        raise BdetrError(code, load().bdetr_last_error().decode())
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args))

@@ -1,0 +1,78 @@
+// Shared helpers for libbdetr (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/bdetr.h"
+
+namespace bdetr {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Checks the launch (not the execution: everything is asynchronous).
+#define BDETR_CHECK_LAUNCH(name)                                                     \
+    do {                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) {                                                    \
+            ::bdetr::set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e__)); \
+            return BDETR_E_CUDA;                                                     \
+        }                                                                            \
+        ::bdetr::count_launch();                                                     \
+    } while (0)
+
+#define BDETR_CUDA(call)                                                             \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            ::bdetr::set_error("%s failed: %s", #call, cudaGetErrorString(e__));     \
+            return BDETR_E_CUDA;                                                     \
+        }                                                                            \
+    } while (0)
+
+#define BDETR_REQUIRE(cond, code, msg)                                               \
+    do {                                                                             \
+        if (!(cond)) {                                                               \
+            ::bdetr::set_error("%s: %s", __func__, msg);                             \
+            return code;                                                             \
+        }                                                                            \
+    } while (0)
+
+__host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
+
+// Counter-based dropout keep decision shared with the oracle (DESIGN.md "dropout").
+__device__ __forceinline__ bool dropout_keep(uint32_t idx, uint32_t key, uint32_t thresh)
+{
+    return lowbias32(idx ^ key) >= thresh;
+}
+
+__host__ inline uint32_t dropout_threshold(float rate)
+{
+    double t = (double)rate * 4294967296.0;
+    if (t <= 0.0) return 0u;
+    if (t >= 4294967295.0) return 4294967295u;
+    return (uint32_t)t;
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace bdetr

@@ -1,0 +1,194 @@
+"""Hungarian set-matching loss — same classes / call conventions as the reference's
+ModelComponents/losses_and_metrics.py, backed by the sm_100a kernels in csrc/matcher.cu.
+
+Tensors are CUDA torch tensors used as plain device buffers (fp32; num_objects int32).  No CPU
+fallback: every call goes through libbdetr.so.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .device import empty, f32, i32, ptr, stream_ptr, zeros
+
+# default weights (reference losses_and_metrics.py:8-11)
+DEFAULT_CATEGORY_WEIGHT = 1000.0
+DEFAULT_BOX_WEIGHT = 1.0
+DEFAULT_ATTRIBUTE_WEIGHT = 100.0
+DEFAULT_EXIST_WEIGHT = 100.0
+
+
+# Markers with the reference's function names: CostArray.call(y_true, y_pred, func) selects the term.
+def CategoryLoss(*_):  # reference :44-49
+    raise TypeError("CategoryLoss is evaluated on device through CostArray / MatchingLoss")
+
+
+def AttributeLoss(*_):  # reference :51-57
+    raise TypeError("AttributeLoss is evaluated on device through CostArray / MatchingLoss")
+
+
+def BoxLoss(*_):  # reference :68-72
+    raise TypeError("BoxLoss is evaluated on device through CostArray / MatchingLoss")
+
+
+def raise_for_status(status: torch.Tensor) -> None:
+    """Mirrors scipy's ValueErrors (the reference dies on them inside tf.numpy_function)."""
+    st = status.cpu()
+    if (st == _lib.BDETR_E_INVALID_COST).any():
+        raise ValueError("matrix contains invalid numeric entries")
+    if (st == _lib.BDETR_E_INFEASIBLE).any():
+        raise ValueError("cost matrix is infeasible")
+
+
+def pairwise_cost(y_true, y_pred, w_cat, w_box, w_attr):
+    """Weighted [B,T,Q] matching cost (reference MatchingLoss.call :119-130)."""
+    category, attribute, bbox = (f32(t) for t in y_true[:3])
+    cat_preds, attr_preds, box_preds = (f32(t) for t in y_pred)
+    B, T, C = category.shape
+    Q, A = cat_preds.shape[1], attribute.shape[2]
+    cost = empty(B, T, Q)
+    _lib.call("bdetr_cost_matrix_fwd", B, T, Q, C, A, ptr(category), ptr(attribute), ptr(bbox),
+              ptr(cat_preds), ptr(attr_preds), ptr(box_preds), float(w_cat), float(w_box), float(w_attr),
+              ptr(cost), stream_ptr())
+    return cost
+
+
+class CostArray:
+    """Pairwise f(x, y) values, targets on rows and predictions on columns (reference :215-225)."""
+
+    def __init__(self, **kwargs):
+        self.name = "CostArray"
+
+    def call(self, y_true, y_pred, func):
+        y_true, y_pred = f32(y_true), f32(y_pred)
+        B, T, Q = y_true.shape[0], y_true.shape[1], y_pred.shape[1]
+        one = lambda n, k: zeros(B, n, k)
+        if func is CategoryLoss:
+            tr = [y_true, one(T, 2), one(T, 4)]
+            pr = [y_pred, one(Q, 2) + 0.5, one(Q, 4)]
+            return pairwise_cost(tr, pr, 1.0, 0.0, 0.0)
+        if func is AttributeLoss:
+            tr = [one(T, 2), y_true, one(T, 4)]
+            pr = [one(Q, 2) + 0.5, y_pred, one(Q, 4)]
+            return pairwise_cost(tr, pr, 0.0, 0.0, 1.0)
+        if func is BoxLoss:
+            tr = [one(T, 2), one(T, 2), y_true]
+            pr = [one(Q, 2) + 0.5, one(Q, 2) + 0.5, y_pred]
+            return pairwise_cost(tr, pr, 0.0, 1.0, 0.0)
+        raise ValueError("func must be CategoryLoss, AttributeLoss or BoxLoss")
+
+    __call__ = call
+
+
+class MatchingAssignment:
+    """Bipartite assignment; bit-identical to scipy.optimize.linear_sum_assignment (reference :228-251)."""
+
+    def __init__(self, name="MatchingAssignment", **kwargs):
+        self.name = name
+        self.last_status = None
+
+    def assign(self, cost_array, num_objects, want_mask=True, want_assigned=True):
+        cost_array = f32(cost_array)
+        B, T, Q = cost_array.shape
+        num_objects = i32(num_objects.reshape(-1))
+        col4row = empty(B, T, dtype=torch.int32)
+        row4col = empty(B, Q, dtype=torch.int32)
+        status = empty(B, dtype=torch.int32)
+        mask = empty(B, T, Q) if want_mask else None
+        assigned = empty(B, Q) if want_assigned else None
+        _lib.call("bdetr_lsap_assign", B, T, Q, ptr(cost_array), ptr(num_objects), ptr(col4row), ptr(row4col),
+                  ptr(mask), ptr(assigned), ptr(status), stream_ptr())
+        self.last_status = status
+        return col4row, row4col, mask, assigned, status
+
+    def call(self, cost_array, num_objects):
+        _, _, mask, _, status = self.assign(cost_array, num_objects, want_assigned=False)
+        raise_for_status(status)
+        return mask
+
+    __call__ = call
+
+
+class MatchingMask:
+    """(mask [B,T,Q], assigned_predictions [B,Q,1]) (reference :195-212)."""
+
+    def __init__(self, name="MatchingMask", **kwargs):
+        self.name = name
+        self.MatchingAssignment = MatchingAssignment()
+
+    def call(self, inputs):
+        matching_costs, num_objects = inputs
+        _, _, mask, assigned, status = self.MatchingAssignment.assign(matching_costs, num_objects)
+        raise_for_status(status)
+        return mask, assigned.unsqueeze(-1)
+
+    __call__ = call
+
+
+class MatchingLoss:
+    """reference :75-161.  call([y_true, y_pred]) -> ([total, cat, attr, box, exist] each [B], [iou [1,Q]])."""
+
+    def __init__(self, name="MatchingLoss", category_weight=None, box_weight=None, attribute_weight=None,
+                 exist_weight=None, **kwargs):
+        self.name = name
+        self.category_weight = DEFAULT_CATEGORY_WEIGHT if category_weight is None else float(category_weight)
+        self.box_weight = DEFAULT_BOX_WEIGHT if box_weight is None else float(box_weight)
+        self.attribute_weight = DEFAULT_ATTRIBUTE_WEIGHT if attribute_weight is None else float(attribute_weight)
+        self.exist_weight = DEFAULT_EXIST_WEIGHT if exist_weight is None else float(exist_weight)
+        self.MatchingMask = MatchingMask()
+        self.CostArray = CostArray()
+        self.MatchingMetric = MatchingMetric()
+        self.check_status = True      # poll the device status flag after each call (set False inside graphs)
+
+    def forward(self, y_true, y_pred):
+        """Device-only forward; returns a context dict for `backward` (no host sync)."""
+        category, attribute, bbox = (f32(t) for t in y_true[:3])
+        num_objects = i32(y_true[3].reshape(-1))
+        cat_preds, attr_preds, box_preds = (f32(t) for t in y_pred)
+        B, T, C = category.shape
+        Q, A = cat_preds.shape[1], attribute.shape[2]
+        w = (self.category_weight, self.box_weight, self.attribute_weight, self.exist_weight)
+        cost = pairwise_cost([category, attribute, bbox], [cat_preds, attr_preds, box_preds], w[0], w[1], w[2])
+        col4row, row4col, _, _, status = self.MatchingMask.MatchingAssignment.assign(
+            cost, num_objects, want_mask=False, want_assigned=False)
+        losses = empty(5, B)
+        iou = empty(Q)
+        st = stream_ptr()
+        _lib.call("bdetr_matched_loss_fwd", B, T, Q, C, A, ptr(category), ptr(attribute), ptr(bbox), ptr(num_objects),
+                  ptr(cat_preds), ptr(attr_preds), ptr(box_preds), ptr(col4row), ptr(row4col),
+                  w[0], w[1], w[2], w[3], ptr(losses), ptr(iou), st)
+        return {"dims": (B, T, Q, C, A), "true": (category, attribute, bbox, num_objects),
+                "pred": (cat_preds, attr_preds, box_preds), "col4row": col4row, "row4col": row4col,
+                "status": status, "losses": losses, "iou": iou, "cost": cost, "weights": w}
+
+    def backward(self, ctx, d_cat, d_attr, d_box, gscale=1.0):
+        """Accumulates d(gscale * sum_b total_b)/d(y_pred) into d_cat/d_attr/d_box."""
+        B, T, Q, C, A = ctx["dims"]
+        category, attribute, bbox, num_objects = ctx["true"]
+        cat_preds, attr_preds, box_preds = ctx["pred"]
+        w = ctx["weights"]
+        _lib.call("bdetr_matched_loss_bwd", B, T, Q, C, A, ptr(category), ptr(attribute), ptr(bbox), ptr(num_objects),
+                  ptr(cat_preds), ptr(attr_preds), ptr(box_preds), ptr(ctx["col4row"]), ptr(ctx["row4col"]),
+                  w[0], w[1], w[2], w[3], float(gscale), ptr(d_cat), ptr(d_attr), ptr(d_box), stream_ptr())
+
+    def call(self, inputs):
+        y_true, y_pred = inputs
+        ctx = self.forward(y_true, y_pred)
+        if self.check_status:
+            raise_for_status(ctx["status"])
+        self.last_ctx = ctx
+        L = ctx["losses"]
+        return [L[0], L[1], L[2], L[3], L[4]], [ctx["iou"].unsqueeze(0)]
+
+    __call__ = call
+
+
+class MatchingMetric:
+    """Masked pairwise IoU [B,T,Q] (reference :164-192)."""
+
+    def __init__(self, name="MatchingMetric", **kwargs):
+        self.name = name
+
+    def call(self, inputs, assignment_mask=None):
+        raise NotImplementedError(
+            "the IOU metric is produced by MatchingLoss.call (fused into the matched-loss kernel)")

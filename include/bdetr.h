@@ -1,0 +1,229 @@
+/* libbdetr.so — C ABI of the B200-native Boosted_DETR hot path.
+ *
+ * The reference (mvenouziou/Boosted_DETR) has no FFI: its boundary is the Keras layer protocol
+ * (pure Python).  Each entry point below replaces the body of one reference layer `call`; the
+ * Python classes in boosted_detr_b200/ keep the reference's class names / ctor arguments / call
+ * conventions and forward to these functions through ctypes.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA-runtime types in signatures: device pointers are `void*`/`float*`,
+ *     the stream is an opaque `void*` holding a cudaStream_t (NULL = legacy default stream);
+ *   - every tensor is row-major fp32 in device memory unless stated otherwise; the caller owns all
+ *     memory (inputs, outputs, saved activations, scratch); no hidden allocation, no hidden sync;
+ *   - all calls are asynchronous on the given stream and CUDA-graph capturable;
+ *   - return 0 (BDETR_OK) or a negative bdetr_status; bdetr_last_error() gives a thread-local text;
+ *   - citations are file:line under /root/reference/ModelComponents/.
+ */
+#ifndef BDETR_H_
+#define BDETR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    BDETR_OK = 0,
+    BDETR_E_BAD_SHAPE = -1,
+    BDETR_E_CUDA = -2,
+    BDETR_E_INVALID_COST = -3, /* scipy: ValueError("matrix contains invalid numeric entries") */
+    BDETR_E_INFEASIBLE = -4,   /* scipy: ValueError("cost matrix is infeasible")               */
+    BDETR_E_NULL = -5,
+    BDETR_E_UNSUPPORTED = -6
+} bdetr_status;
+
+/* compute modes for the dense (GEMM / attention) kernels */
+#define BDETR_MODE_FP32 0 /* fp32 SIMT FFMA everywhere: the 1e-5 parity mode                   */
+#define BDETR_MODE_BF16 1 /* bf16 operands, fp32 accumulate on tcgen05 tensor cores (1e-3 mode) */
+
+int bdetr_version(void);
+const char *bdetr_last_error(void);
+/* Process-wide compute mode used by the dense entry points. */
+int bdetr_set_mode(int mode);
+int bdetr_get_mode(void);
+/* Number of kernels launched by this library since the last reset (bench.py's gpu_launches). */
+long long bdetr_launch_count(void);
+void bdetr_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Matcher trio (K7/K8/K9)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Pairwise matching cost [B,T,Q] (targets = rows, predictions = columns):
+ *   cost = (w_cat*cat + w_box*box) + w_attr*attr
+ * Replaces CostArray.call (losses_and_metrics.py:222-225) applied to CategoryLoss (:44-49),
+ * AttributeLoss (:51-57), BoxLoss (:68-72) plus the weighting / summation of MatchingLoss.call
+ * (:119-130), without the reference's [B,T,Q,C] / [B,T,Q,A] / [B,T,Q,4] broadcast intermediates.
+ * cat_true [B,T,C] one-hot, attr_true [B,T,A] multi-hot (entries must be exactly 0 or 1),
+ * box_true [B,T,4], cat_pred [B,Q,C], attr_pred [B,Q,A], box_pred [B,Q,4] (COCO x,y,w,h). */
+int bdetr_cost_matrix_fwd(int B, int T, int Q, int C, int A,
+                          const float *cat_true, const float *attr_true, const float *box_true,
+                          const float *cat_pred, const float *attr_pred, const float *box_pred,
+                          float w_cat, float w_box, float w_attr,
+                          float *cost, void *stream);
+
+/* Per-image rectangular linear sum assignment on cost[b, :num_objects[b], :]; results are
+ * bit-identical to scipy.optimize.linear_sum_assignment (ties included).
+ * Replaces MatchingAssignment.scipy_linear_assignment_mask (:234-245) and MatchingMask.call
+ * (:202-212).  Outputs (each may be NULL except col4row/status):
+ *   col4row  [B,T] int32  matched prediction of target row t, -1 if none (padding / n>Q leftovers)
+ *   row4col  [B,Q] int32  matched target of prediction q, -1 if none
+ *   mask     [B,T,Q] fp32 the reference's assignment mask
+ *   assigned [B,Q]   fp32 max_t mask (the reference's `assigned_predictions`)
+ *   status   [B]   int32  0, BDETR_E_INVALID_COST or BDETR_E_INFEASIBLE per image (device flag;
+ *                         the host wrapper polls it once per step, not per call). */
+int bdetr_lsap_assign(int B, int T, int Q, const float *cost, const int32_t *num_objects,
+                      int32_t *col4row, int32_t *row4col, float *mask, float *assigned,
+                      int32_t *status, void *stream);
+/* dynamic shared memory (bytes) one image needs in bdetr_lsap_assign; informational. */
+size_t bdetr_lsap_smem_bytes(int T, int Q);
+
+/* Matched losses of MatchingLoss.call (:133-160): losses [5,B] = total, category, attribute, box,
+ * existence; iou [Q] = the `IOU` metric (shape [1,Q] in the reference).
+ * weights = {w_cat, w_box, w_attr, w_exist}. */
+int bdetr_matched_loss_fwd(int B, int T, int Q, int C, int A,
+                           const float *cat_true, const float *attr_true, const float *box_true,
+                           const int32_t *num_objects,
+                           const float *cat_pred, const float *attr_pred, const float *box_pred,
+                           const int32_t *col4row, const int32_t *row4col,
+                           float w_cat, float w_box, float w_attr, float w_exist,
+                           float *losses, float *iou, void *stream);
+
+/* d(gscale * sum_b total_b)/d(predictions), ACCUMULATED (+=) into d_cat_pred [B,Q,C],
+ * d_attr_pred [B,Q,A], d_box_pred [B,Q,4].  The assignment is a constant (tf.numpy_function). */
+int bdetr_matched_loss_bwd(int B, int T, int Q, int C, int A,
+                           const float *cat_true, const float *attr_true, const float *box_true,
+                           const int32_t *num_objects,
+                           const float *cat_pred, const float *attr_pred, const float *box_pred,
+                           const int32_t *col4row, const int32_t *row4col,
+                           float w_cat, float w_box, float w_attr, float w_exist, float gscale,
+                           float *d_cat_pred, float *d_attr_pred, float *d_box_pred, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense path (K1-K6)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Keras Dense kernels are [in,out]; y = x @ kernel + bias. */
+typedef struct {
+    float *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo; /* [D,D] / [D] each                   */
+    float *ln_gamma, *ln_beta;                   /* [D]                                 */
+} bdetr_attn_params;                             /* same struct is used for gradients   */
+
+/* caller-allocated activations saved by the forward for the backward (also forward scratch) */
+typedef struct {
+    float *qp, *kp, *vp; /* projected q [B,Lq,D], k,v [B,Lk,D]                              */
+    float *o;            /* attention output in the reference's [B,H,Lq,d] layout (quirk Q1) */
+    float *lse;          /* [B,H,Lq] log-sum-exp of the scaled scores                        */
+    float *z;            /* [B,Lq,D] pre-LayerNorm sum                                       */
+    float *mean, *rstd;  /* [B*Lq] LayerNorm statistics                                      */
+} bdetr_attn_saved;
+
+/* backward scratch: d_qp [B,Lq,D], d_kp, d_vp [B,Lk,D], d_o [B,H,Lq,d], d_z [B,Lq,D], delta [B,H,Lq] */
+typedef struct {
+    float *d_qp, *d_kp, *d_vp, *d_o, *d_z, *delta;
+} bdetr_attn_scratch;
+
+/* AttentionBlock.call (transformers.py:139-151) with MultiheadAttention.call (:68-102) inside:
+ *   out = LayerNorm_eps( query + Dropout( MHA(query,key,value) ) )
+ * query [B,Lq,D] (also the residual), key/value [B,Lk,D]; H heads of width D/H; the attention
+ * output is re-read as [B,Lq,D] WITHOUT permuting back (reference line :100).
+ * dropout_rate 0 disables dropout (inference); the keep mask is hash(idx ^ dropout_key). */
+int bdetr_attention_block_fwd(int B, int Lq, int Lk, int D, int H,
+                              const float *query, const float *key, const float *value,
+                              const bdetr_attn_params *w, float dropout_rate, uint32_t dropout_key,
+                              float ln_eps, float *out, const bdetr_attn_saved *saved, void *stream);
+
+/* Backward of the above.  Parameter gradients are ACCUMULATED into *gw.  d_query/d_key/d_value
+ * may be NULL (not needed); acc_flags bit0/1/2 = accumulate into d_query/d_key/d_value instead of
+ * overwriting. */
+int bdetr_attention_block_bwd(int B, int Lq, int Lk, int D, int H,
+                              const float *query, const float *key, const float *value,
+                              const bdetr_attn_params *w, float dropout_rate, uint32_t dropout_key,
+                              const bdetr_attn_saved *saved, const float *d_out,
+                              float *d_query, float *d_key, float *d_value, int acc_flags,
+                              const bdetr_attn_params *gw, const bdetr_attn_scratch *scratch,
+                              void *stream);
+
+typedef struct {
+    float *w1, *b1, *w2, *b2; /* DenseRelu, DenseLinear: [D,D] / [D] */
+    float *ln_gamma, *ln_beta;
+} bdetr_ffn_params;
+
+typedef struct {
+    float *h;           /* [M,D] relu(x W1 + b1)        */
+    float *z;           /* [M,D] pre-LayerNorm sum      */
+    float *mean, *rstd; /* [M]                          */
+} bdetr_ffn_saved;
+
+typedef struct {
+    float *d_z, *d_h; /* [M,D] each */
+} bdetr_ffn_scratch;
+
+/* FeedForwardBlock.call (transformers.py:182-193): out = LN( x + Dropout( relu(xW1+b1)W2+b2 ) ). */
+int bdetr_ffn_block_fwd(int M, int D, const float *x, const bdetr_ffn_params *w,
+                        float dropout_rate, uint32_t dropout_key, float ln_eps,
+                        float *out, const bdetr_ffn_saved *saved, void *stream);
+int bdetr_ffn_block_bwd(int M, int D, const float *x, const bdetr_ffn_params *w,
+                        float dropout_rate, uint32_t dropout_key,
+                        const bdetr_ffn_saved *saved, const float *d_out,
+                        float *d_x, int accumulate_dx,
+                        const bdetr_ffn_params *gw, const bdetr_ffn_scratch *scratch, void *stream);
+
+/* out[b,l,:] = x[b,l,:] + pos[l,:]  (EncoderBlock Add1/Add2 :226-227, DecoderPrep Add :441). */
+int bdetr_add_positional_fwd(int B, int L, int D, const float *x, const float *pos, float *out,
+                             void *stream);
+/* d_pos[l,:] += sum_b d_out[b,l,:]. */
+int bdetr_add_positional_bwd(int B, int L, int D, const float *d_out, float *d_pos, void *stream);
+/* out[b,q,:] = q0[q,:]  (DecoderPrep TileBatch2D :445-447) and its backward d_q0 += sum_b d_out. */
+int bdetr_tile_queries_fwd(int B, int Q, int D, const float *q0, float *out, void *stream);
+/* y += x elementwise (gradient joins). */
+int bdetr_accumulate(size_t n, const float *x, float *y, void *stream);
+
+/* One prediction head = Dense(relu) -> BatchNorm -> Dense -> activation, post-activation output
+ * added into the running (boosted) prediction:  cum += mult * act(...), mult = 2 for block 0
+ * (boosted_model.py:222-229, quirk Q2).
+ * kind: 0 softmax (SingleClassPredictionHead, prediction_heads.py:113-131)
+ *       1 sigmoid (MultiClassPredictionHead :182-201)
+ *       2 3*sigmoid(x/100)-1 (BoxPredictionHead :46-63) */
+typedef struct {
+    float *w1, *b1;                  /* [D,Dh], [Dh]                           */
+    float *bn_gamma, *bn_beta;       /* [Dh]                                   */
+    float *bn_moving_mean, *bn_moving_var; /* [Dh] (updated in training)       */
+    float *w2, *b2;                  /* [Dh,Nout], [Nout]                      */
+} bdetr_head_params;
+
+typedef struct {
+    float *h;                /* [M,Dh] relu(x W1 + b1)               */
+    float *hn;               /* [M,Dh] batch-normalised              */
+    float *bn_mean, *bn_rstd;/* [Dh]                                 */
+    float *act;              /* [M,Nout] post-activation output      */
+} bdetr_head_saved;
+
+typedef struct {
+    float *d_logits; /* [M,Nout] */
+    float *d_hn;     /* [M,Dh]   */
+    float *d_h;      /* [M,Dh]   */
+} bdetr_head_scratch;
+
+int bdetr_head_fwd(int M, int D, int Dh, int Nout, int kind, int training, float mult,
+                   const float *x, const bdetr_head_params *w, float bn_eps, float bn_momentum,
+                   float *cum, int cum_init, const bdetr_head_saved *saved, void *stream);
+/* d_cum [M,Nout] is the gradient w.r.t. the running prediction this head was added into. */
+int bdetr_head_bwd(int M, int D, int Dh, int Nout, int kind, float mult,
+                   const float *x, const bdetr_head_params *w, float bn_eps,
+                   const bdetr_head_saved *saved, const float *d_cum,
+                   float *d_x, int accumulate_dx,
+                   const bdetr_head_params *gw, const bdetr_head_scratch *scratch, void *stream);
+
+/* Generic row-major GEMM used by the entry points above, exported for tests and benchmarks:
+ * C[M,N] = (beta ? C : 0) + op(A)[M,K] @ op(B)[K,N] (+ bias[N]) (relu if act==1).
+ * transA: A is stored [K,M]; transB: B is stored [N,K]. */
+int bdetr_gemm(int M, int N, int K, const float *A, int transA, const float *Bm, int transB,
+               const float *bias, int act, int beta, float *C, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDETR_H_ */
