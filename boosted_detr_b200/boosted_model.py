@@ -1,0 +1,304 @@
+"""BoostedDETR — the reference's ModelComponents/boosted_model.py hot loop (call :170-267) on sm_100a.
+
+Scope: the model starts at the BackboneNeck output.  `inputs` is a dict with
+  'features'    [B, rows, cols, encoder_dim]  fp32   (replaces 'image'; backbone is out of scope)
+  'category'    [B, T, C] one-hot  fp32              (the reference's Tokenization output)
+  'attribute'   [B, T, A] multi-hot fp32
+  'bbox'        [B, T, 4] COCO x,y,w,h, padded with -10
+  'num_objects' [B] or [B,1] int
+Values may be numpy arrays (copied host->device through pinned staging) or CUDA tensors.
+The Keras surface is kept: BoostedDETR(**params), call(inputs, training), compile(optimizer), fit(ds),
+train_step / test_step (which, as in the reference :269-270, also trains), per-block layer lists with
+`trainable` flags, get_config().
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device import empty, f32, i32, ptr, require_cuda, stream_ptr, zeros
+from .layers import Layer, dropout_key
+from .losses_and_metrics import MatchingLoss, raise_for_status
+from .prediction_heads import BoxPredictionHead, MultiClassPredictionHead, SingleClassPredictionHead
+from .transformers import (DecoderBlock, DecoderBlock_NoSelfAttention, DecoderPrep, ImageEncoderAttention, accumulate)
+
+# dropout site ids, one per Keras Dropout instance: block i -> 8*i + k
+SITE_ENC_ATTN, SITE_ENC_FFN, SITE_DEC_SELF, SITE_DEC_CROSS, SITE_DEC_FFN = 0, 1, 2, 3, 4
+BACKBONE_STRIDE = 32   # EfficientNetB4 include_top=False (reference backbone.py:28-31)
+
+
+class BoostedDETR:
+    def __init__(self, num_object_preds, image_size, num_encoder_blocks, num_encoder_heads, encoder_dim,
+                 num_decoder_blocks, num_decoder_heads, decoder_dim, num_panoptic_heads=1, panoptic_dim=32,
+                 vocab_dict=None, classification_only=False, attribute_weight=1.0, name="DETR",
+                 feature_shape=None, seed=0, **kwargs):
+        self.name = name
+        self.use_intermediate_predictions = True
+        self.num_object_preds = num_object_preds
+        self.image_size = tuple(image_size)
+        self.num_encoder_blocks = num_encoder_blocks      # ignored by the reference too (:86, quirk Q5)
+        self.num_encoder_heads = num_encoder_heads
+        self.encoder_dim = encoder_dim
+        self.num_decoder_blocks = num_decoder_blocks
+        self.num_decoder_heads = num_decoder_heads
+        self.decoder_dim = decoder_dim
+        self.num_panoptic_heads = num_panoptic_heads
+        self.panoptic_dim = panoptic_dim
+        self.vocab_dict = vocab_dict or {"category": [], "attribute": []}
+        self.classification_only = classification_only
+        # vocab sizes include <PAD> and <OOV> (reference tokenizers.py:32-33)
+        self.num_categories = len(self.vocab_dict["category"]) + 2
+        self.num_attributes = len(self.vocab_dict["attribute"]) + 2
+        self.feature_shape = tuple(feature_shape) if feature_shape else (
+            self.image_size[0] // BACKBONE_STRIDE, self.image_size[1] // BACKBONE_STRIDE)
+
+        Layer._rng = np.random.default_rng(seed)
+        N = num_decoder_blocks
+        self.EncoderTransformerBlocks = [ImageEncoderAttention(1, num_encoder_heads, name=f"ImageEncoderAttention_{i}")
+                                         for i in range(N)]
+        self.DecoderPrep = DecoderPrep(num_object_preds, decoder_dim, name="DecoderPrep")
+        self.DecoderBlocks = [DecoderBlock_NoSelfAttention(num_decoder_heads, name="DecoderBlock_0")]
+        self.DecoderBlocks += [DecoderBlock(num_decoder_heads, name=f"DecoderBlock_{i}") for i in range(1, N)]
+        self.CategoryBlocks = [SingleClassPredictionHead(self.num_categories, decoder_dim, num_object_preds,
+                                                         name=f"CategoryPredictionHead_{i}") for i in range(N)]
+        self.AttributeBlocks = [MultiClassPredictionHead(self.num_attributes, decoder_dim, num_object_preds,
+                                                         name=f"AttributePredictionHead_{i}") for i in range(N)]
+        self.BoxBlocks = [BoxPredictionHead(decoder_dim, num_object_preds, name=f"BoxPredictionHead_{i}")
+                          for i in range(N)]
+        self.loss_fn = MatchingLoss(category_weight=None, box_weight=0.0 if classification_only else None,
+                                    attribute_weight=attribute_weight, exist_weight=None, name="MatchingLoss")
+        self.optimizer = None
+        self.dropout_seed = None          # None: dropout off (parity runs); int: hash-mask dropout, rate .1
+        self.step_count = 0
+        self.num_replicas = 1
+        self.grad_allreduce = None        # set by parallel.DataParallel
+        self._flat = None
+        self.metrics_names = ["loss", "Category_Loss", "Attribute_Loss", "Box_Loss", "Existence_Loss", "IOU"]
+
+    # -- structure -----------------------------------------------------------------------------
+    def layers(self):
+        return [*self.EncoderTransformerBlocks, self.DecoderPrep, *self.DecoderBlocks, *self.CategoryBlocks,
+                *self.AttributeBlocks, *self.BoxBlocks]
+
+    def get_config(self):
+        return {k: getattr(self, k) for k in ("num_object_preds", "image_size", "num_encoder_blocks", "num_encoder_heads",
+                                              "encoder_dim", "num_decoder_blocks", "num_decoder_heads", "decoder_dim",
+                                              "num_panoptic_heads", "panoptic_dim", "vocab_dict")}
+
+    def named_weights(self):
+        for layer in self.layers():
+            yield from layer.named_weights()
+
+    def build(self, batch_size=2):
+        """Creates all weights by running one tiny inference call (Keras builds lazily the same way)."""
+        R, Cc = self.feature_shape
+        self.call({"features": zeros(batch_size, R, Cc, self.encoder_dim)}, training=False)
+        self._flatten()
+        return self
+
+    def _flatten(self):
+        """Moves trainable weights / gradients into two flat buffers (one memset, one all-reduce)."""
+        named = [(n, o, k) for n, o, k in self.named_weights() if k not in o._non_trainable]
+        self._index, off = {}, 0
+        for n, o, k in named:
+            w = o._weights[k]
+            self._index[n] = (off, w.numel(), tuple(w.shape))
+            off += (w.numel() + 3) // 4 * 4               # keep every tensor 16-byte aligned
+        flat_w, flat_g = zeros(off), zeros(off)
+        for n, o, k in named:
+            o0, cnt, shp = self._index[n]
+            flat_w[o0:o0 + cnt].copy_(o._weights[k].reshape(-1))
+            o._weights[k] = flat_w[o0:o0 + cnt].view(shp)
+            o._grads[k] = flat_g[o0:o0 + cnt].view(shp)
+        self._flat = (flat_w, flat_g)
+        for layer in self.layers():
+            layer.invalidate()
+
+    def num_parameters(self, include_non_trainable=True):
+        return sum(o._weights[k].numel() for _, o, k in self.named_weights()
+                   if include_non_trainable or k not in o._non_trainable)
+
+    def get_weights_dict(self):
+        return {n: o._weights[k].detach().cpu().numpy().copy() for n, o, k in self.named_weights()}
+
+    def set_weights_dict(self, d):
+        for n, o, k in self.named_weights():
+            if n in d:
+                o._weights[k].copy_(torch.from_numpy(np.ascontiguousarray(d[n], np.float32)).to(o._weights[k].device))
+
+    def get_grads_dict(self):
+        return {n: o._grads[k].detach().cpu().numpy().copy() for n, o, k in self.named_weights() if k in o._grads}
+
+    def zero_grads(self):
+        if self._flat is not None:
+            self._flat[1].zero_()
+        else:
+            for _, o, k in self.named_weights():
+                if k in o._grads:
+                    o._grads[k].zero_()
+
+    # -- inputs --------------------------------------------------------------------------------
+    def _to_device(self, name, x, dtype):
+        """numpy -> persistent pinned staging buffer -> HBM (async on the current stream)."""
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            return i32(x) if dtype == "i32" else f32(x)
+        arr = x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+        arr = np.ascontiguousarray(arr, dtype=np.int32 if dtype == "i32" else np.float32)
+        stage = getattr(self, "_staging", None)
+        if stage is None:
+            stage = self._staging = {}
+        key = (name, arr.shape)
+        if key not in stage:
+            stage[key] = torch.empty(arr.shape, dtype=torch.int32 if dtype == "i32" else torch.float32).pin_memory()
+        stage[key].numpy()[...] = arr
+        self.h2d_bytes += arr.nbytes
+        return stage[key].to(require_cuda(), non_blocking=True)
+
+    def _prepare(self, inputs, training):
+        self.h2d_bytes = 0
+        feats = self._to_device("features", inputs["features"], "f32")
+        y_true = None
+        if training:
+            y_true = [self._to_device("category", inputs["category"], "f32"),
+                      self._to_device("attribute", inputs["attribute"], "f32"),
+                      self._to_device("bbox", inputs["bbox"], "f32"),
+                      self._to_device("num_objects", inputs["num_objects"], "i32").reshape(-1)]
+        return feats, y_true
+
+    def _keys(self, i):
+        if self.dropout_seed is None:
+            return None
+        k = lambda s: dropout_key(self.dropout_seed, 8 * i + s)
+        return {"enc": [(k(SITE_ENC_ATTN), k(SITE_ENC_FFN))], "dec": (k(SITE_DEC_SELF), k(SITE_DEC_CROSS), k(SITE_DEC_FFN))}
+
+    # -- forward -------------------------------------------------------------------------------
+    def forward(self, feats, y_true, training):
+        """The hot loop (reference :199-246).  Returns (y_pred, ctx)."""
+        N = self.num_decoder_blocks
+        use_dropout = training and self.dropout_seed is not None
+        x = feats
+        cums = None
+        blocks, loss_ctxs = [], []
+        for i in range(N):
+            keys = self._keys(i) if use_dropout else None
+            enc = self.EncoderTransformerBlocks[i]
+            for blk in enc.EncoderBlocks:
+                blk.SelfAttentionBlock.rate = blk.FeedForwardBlock.rate = 0.1 if use_dropout else 0.0
+            dec_l = self.DecoderBlocks[i]
+            for nm in ("SelfAttentionBlock", "JointAttentionBlock", "FeedForwardBlock"):
+                if hasattr(dec_l, nm):
+                    getattr(dec_l, nm).rate = 0.1 if use_dropout else 0.0
+            (x, pos), c_enc = enc.forward([x], training, keys["enc"] if keys else None)
+            prep_out, c_prep = self.DecoderPrep.forward([x, pos], training)
+            dec, c_dec = dec_l.forward(list(prep_out), training, keys["dec"] if keys else (0, 0, 0))
+            mult = 2.0 if i == 0 else 1.0                 # block 0 is counted twice (reference :222-229)
+            if cums is not None and training:
+                cums = [c.clone() for c in cums]          # each block's loss keeps its own running prediction
+            heads = (self.CategoryBlocks[i], self.AttributeBlocks[i], self.BoxBlocks[i])
+            c_heads, new_cums = [], []
+            for h, head in enumerate(heads):
+                _, c = head.forward([dec], training, cum=None if cums is None else cums[h], mult=mult)
+                c_heads.append(c)
+                new_cums.append(c["cum"])
+            cums = new_cums
+            blocks.append({"enc": c_enc, "prep": c_prep, "dec": c_dec, "heads": c_heads})
+            if training:
+                loss_ctxs.append(self.loss_fn.forward(y_true, cums))
+        return cums, {"blocks": blocks, "loss": loss_ctxs, "y_true": y_true}
+
+    def backward(self, ctx, gscale=1.0):
+        """Gradient of gscale * sum_b sum_i total_b^(i) w.r.t. every trainable weight (accumulated)."""
+        N = self.num_decoder_blocks
+        first = ctx["loss"][0]
+        B, T, Q, C, A = first["dims"]
+        r_cat, r_attr, r_box = zeros(B, Q, C), zeros(B, Q, A), zeros(B, Q, 4)
+        d_x_next = None
+        for i in reversed(range(N)):
+            blk = ctx["blocks"][i]
+            self.loss_fn.backward(ctx["loss"][i], r_cat, r_attr, r_box, gscale)
+            d_dec = self.CategoryBlocks[i].backward(blk["heads"][0], r_cat)
+            self.AttributeBlocks[i].backward(blk["heads"][1], r_attr, d_x=d_dec, acc=True)
+            self.BoxBlocks[i].backward(blk["heads"][2], r_box, d_x=d_dec, acc=True)
+            d_ev, d_q, d_ek = self.DecoderBlocks[i].backward(blk["dec"], d_dec)
+            if d_x_next is not None:
+                accumulate(d_x_next.reshape(d_ev.shape), d_ev)
+            enc = self.EncoderTransformerBlocks[i]
+            L, D = d_ev.shape[1], d_ev.shape[2]
+            g_pos = enc._grads["positional_encoding"].view(L, D)
+            d_x4 = self.DecoderPrep.backward(blk["prep"], d_ev, d_q, d_ek, g_pos)
+            d_x_next = enc.backward(blk["enc"], d_x4)
+        return d_x_next
+
+    # -- keras surface -------------------------------------------------------------------------
+    def call(self, inputs, training=False):
+        feats, y_true = self._prepare(inputs, training)
+        y_pred, ctx = self.forward(feats, y_true, training)
+        self.last_ctx = ctx
+        if training:
+            self._collect_metrics(ctx)
+        return y_pred
+
+    __call__ = call
+
+    def _collect_metrics(self, ctx):
+        B = ctx["loss"][0]["dims"][0]
+        tot = zeros(5, B)
+        for c in ctx["loss"]:
+            accumulate(c["losses"], tot)
+        self.losses = [tot[0]]                                # add_loss(loss) (reference :250)
+        self.metric_tensors = {"loss": tot[0], "Category_Loss": tot[1], "Attribute_Loss": tot[2], "Box_Loss": tot[3],
+                               "Existence_Loss": tot[4], "IOU": ctx["loss"][-1]["iou"].unsqueeze(0)}
+        return self.metric_tensors
+
+    def compile(self, optimizer=None, **kwargs):
+        self.optimizer = optimizer
+        if optimizer is not None and self._flat is None:
+            self.build()
+        return self
+
+    def train_step(self, inputs, return_host=True):
+        if self._flat is None:
+            self.build()
+        feats, y_true = self._prepare(inputs, True)
+        self.zero_grads()
+        y_pred, ctx = self.forward(feats, y_true, True)
+        m = self._collect_metrics(ctx)
+        self.backward(ctx, gscale=1.0 / self.num_replicas)
+        if self.grad_allreduce is not None:
+            self.grad_allreduce(self._flat[1])
+        if self.optimizer is not None:
+            self.optimizer.apply(self)
+        self.step_count += 1
+        if self.dropout_seed is not None:
+            self.dropout_seed = (self.dropout_seed + 1) & 0xFFFFFFFF
+        if not return_host:
+            return m
+        for c in ctx["loss"]:
+            raise_for_status(c["status"])
+        return {k: float(v.mean().item()) for k, v in m.items()}
+
+    def test_step(self, inputs):
+        return self.train_step(inputs)          # reference :269-270 (quirk Q8: validation also trains)
+
+    def fit(self, dataset, epochs=1, steps_per_epoch=None, verbose=0, **kwargs):
+        history = {k: [] for k in self.metrics_names}
+        for _ in range(epochs):
+            sums, n = {k: 0.0 for k in self.metrics_names}, 0
+            for step, batch in enumerate(dataset):
+                if steps_per_epoch is not None and step >= steps_per_epoch:
+                    break
+                logs = self.train_step(batch)
+                for k in sums:
+                    sums[k] += logs[k]
+                n += 1
+                if verbose:
+                    print(f"step {step}: " + " ".join(f"{k}={v:.4f}" for k, v in logs.items()))
+            for k in sums:
+                history[k].append(sums[k] / max(n, 1))
+        return history
+
+    def predict_indices(self, inputs):
+        """Numeric half of InverseTokenization (argmax category, attribute >= 0.5) — reference tokenizers.py:130-135."""
+        cat, attr, box = self.call(inputs, training=False)
+        return cat.argmax(dim=-1), attr >= 0.5, box

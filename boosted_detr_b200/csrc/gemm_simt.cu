@@ -1,0 +1,180 @@
+// fp32 SIMT GEMM (FFMA) with fused epilogues: the 1e-5 parity mode of the dense path.
+// 64x64x16 tiles, 256 threads, 4x4 register micro-tile, split-K (atomics) for the weight-gradient
+// shapes whose output is only 256x256.  The bf16 tcgen05 path lives in gemm_umma.cu.
+#include "kernels.cuh"
+
+namespace bdetr {
+
+constexpr int GBM = 64, GBN = 64, GBK = 16, GTHREADS = 256, GPAD = 4;
+
+struct GemmArgs {
+    int M, N, K;
+    const float *A; int lda;
+    const float *B; int ldb;
+    const float *bias; int act; const float *relu_mask; int beta;
+    float *C; int ldc;
+    int k_chunk;          // K range per blockIdx.z
+    int vecA, vecB;       // 16-byte vector loads are legal for this operand
+    int atomic_out;       // split-K: accumulate with atomics (C pre-initialised)
+};
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(GTHREADS)
+gemm_simt_kernel(GemmArgs g)
+{
+    __shared__ __align__(16) float As[2][GBK][GBM + GPAD];
+    __shared__ __align__(16) float Bs[2][GBK][GBN + GPAD];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+    const int kbeg = blockIdx.z * g.k_chunk, kend = min(g.K, kbeg + g.k_chunk);
+    const int tx = tid & 15, ty = tid >> 4;            // 16 x 16 threads, each 4x4 outputs
+    float acc[4][4] = {};
+    float ra[4], rb[4];
+
+    auto load_a = [&](int k0) {
+        if (!TA) {      // A[m, k], k contiguous: thread -> (m = tid/4, 4 consecutive k)
+            const int m = m0 + (tid >> 2), k = k0 + ((tid & 3) << 2);
+            const float *p = g.A + (size_t)m * g.lda + k;
+            if (g.vecA && m < g.M && k + 3 < kend) { const float4 v = *reinterpret_cast<const float4 *>(p); ra[0] = v.x; ra[1] = v.y; ra[2] = v.z; ra[3] = v.w; }
+            else { for (int i = 0; i < 4; ++i) ra[i] = (m < g.M && k + i < kend) ? p[i] : 0.0f; }
+        } else {        // A stored [k, m], m contiguous: thread -> (k = tid/16, 4 consecutive m)
+            const int k = k0 + (tid >> 4), m = m0 + ((tid & 15) << 2);
+            const float *p = g.A + (size_t)k * g.lda + m;
+            if (g.vecA && k < kend && m + 3 < g.M) { const float4 v = *reinterpret_cast<const float4 *>(p); ra[0] = v.x; ra[1] = v.y; ra[2] = v.z; ra[3] = v.w; }
+            else { for (int i = 0; i < 4; ++i) ra[i] = (k < kend && m + i < g.M) ? p[i] : 0.0f; }
+        }
+    };
+    auto load_b = [&](int k0) {
+        if (!TB) {      // B[k, n], n contiguous
+            const int k = k0 + (tid >> 4), n = n0 + ((tid & 15) << 2);
+            const float *p = g.B + (size_t)k * g.ldb + n;
+            if (g.vecB && k < kend && n + 3 < g.N) { const float4 v = *reinterpret_cast<const float4 *>(p); rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; rb[3] = v.w; }
+            else { for (int i = 0; i < 4; ++i) rb[i] = (k < kend && n + i < g.N) ? p[i] : 0.0f; }
+        } else {        // B stored [n, k], k contiguous
+            const int n = n0 + (tid >> 2), k = k0 + ((tid & 3) << 2);
+            const float *p = g.B + (size_t)n * g.ldb + k;
+            if (g.vecB && n < g.N && k + 3 < kend) { const float4 v = *reinterpret_cast<const float4 *>(p); rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; rb[3] = v.w; }
+            else { for (int i = 0; i < 4; ++i) rb[i] = (n < g.N && k + i < kend) ? p[i] : 0.0f; }
+        }
+    };
+    auto store_tiles = [&](int buf) {
+        if (!TA) { const int m = tid >> 2, k = (tid & 3) << 2; for (int i = 0; i < 4; ++i) As[buf][k + i][m] = ra[i]; }
+        else { const int k = tid >> 4, m = (tid & 15) << 2; *reinterpret_cast<float4 *>(&As[buf][k][m]) = make_float4(ra[0], ra[1], ra[2], ra[3]); }
+        if (!TB) { const int k = tid >> 4, n = (tid & 15) << 2; *reinterpret_cast<float4 *>(&Bs[buf][k][n]) = make_float4(rb[0], rb[1], rb[2], rb[3]); }
+        else { const int n = tid >> 2, k = (tid & 3) << 2; for (int i = 0; i < 4; ++i) Bs[buf][k + i][n] = rb[i]; }
+    };
+
+    int buf = 0;
+    if (kbeg < kend) {
+        load_a(kbeg); load_b(kbeg); store_tiles(0);
+        __syncthreads();
+        for (int k0 = kbeg; k0 < kend; k0 += GBK) {
+            const bool more = k0 + GBK < kend;
+            if (more) { load_a(k0 + GBK); load_b(k0 + GBK); }
+#pragma unroll
+            for (int kk = 0; kk < GBK; ++kk) {
+                const float4 a = *reinterpret_cast<const float4 *>(&As[buf][kk][ty << 2]);
+                const float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx << 2]);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            if (more) { store_tiles(buf ^ 1); __syncthreads(); buf ^= 1; }
+        }
+    }
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + (ty << 2) + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + (tx << 2) + j;
+            if (n >= g.N) continue;
+            float v = acc[i][j];
+            float *c = g.C + (size_t)m * g.ldc + n;
+            if (g.atomic_out) {
+                if (g.bias && blockIdx.z == 0) v += g.bias[n];
+                atomicAdd(c, v);
+            } else {
+                if (g.bias) v += g.bias[n];
+                if (g.beta) v += *c;
+                if (g.act == 1) v = fmaxf(v, 0.0f);
+                if (g.relu_mask && !(g.relu_mask[(size_t)m * g.ldc + n] > 0.0f)) v = 0.0f;
+                *c = v;
+            }
+        }
+    }
+}
+
+__global__ void zero_strided_kernel(int M, int N, float *C, int ldc)
+{
+    const size_t total = (size_t)M * N;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
+        C[(e / N) * ldc + (e % N)] = 0.0f;
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int launch_gemm(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB,
+                const float *bias, int act, const float *relu_mask, int beta, float *C, int ldc, cudaStream_t s)
+{
+    BDETR_REQUIRE(M > 0 && N > 0 && K > 0, BDETR_E_BAD_SHAPE, "M,N,K must be positive");
+    BDETR_REQUIRE(A && B && C, BDETR_E_NULL, "null operand");
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.bias = bias; g.act = act;
+    g.relu_mask = relu_mask; g.beta = beta; g.C = C; g.ldc = ldc;
+    g.vecA = aligned16(A) && (lda % 4 == 0);
+    g.vecB = aligned16(B) && (ldb % 4 == 0);
+    const int tiles = ceil_div(M, GBM) * ceil_div(N, GBN);
+    int splits = 1;
+    if (act == 0 && relu_mask == nullptr && tiles < 96 && K >= 512) {
+        splits = min(ceil_div(K, 256), max(1, 296 / tiles));
+    }
+    g.k_chunk = ceil_div(ceil_div(K, splits), GBK) * GBK;
+    splits = ceil_div(K, g.k_chunk);
+    g.atomic_out = splits > 1;
+    if (g.atomic_out && !beta) {
+        zero_strided_kernel<<<min(ceil_div(M * N, 256), 1184), 256, 0, s>>>(M, N, C, ldc);
+        BDETR_CHECK_LAUNCH("zero_strided_kernel");
+    }
+    dim3 grid(ceil_div(N, GBN), ceil_div(M, GBM), splits);
+    if (!TA && !TB) gemm_simt_kernel<false, false><<<grid, GTHREADS, 0, s>>>(g);
+    else if (!TA && TB) gemm_simt_kernel<false, true><<<grid, GTHREADS, 0, s>>>(g);
+    else if (TA && !TB) gemm_simt_kernel<true, false><<<grid, GTHREADS, 0, s>>>(g);
+    else gemm_simt_kernel<true, true><<<grid, GTHREADS, 0, s>>>(g);
+    BDETR_CHECK_LAUNCH("gemm_simt_kernel");
+    return BDETR_OK;
+}
+
+// dst[n] += sum_m src[m,n]: CTA = 32 columns x 8 row-lanes over a row chunk
+__global__ void __launch_bounds__(256)
+colsum_acc_kernel(int M, int N, const float *__restrict__ src, float *__restrict__ dst, int rows_per_cta)
+{
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+    const int rbeg = blockIdx.y * rows_per_cta, rend = min(M, rbeg + rows_per_cta);
+    float s = 0.0f;
+    if (c < N) for (int m = rbeg + r; m < rend; m += 8) s += src[(size_t)m * N + c];
+    red[r][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (r == 0 && c < N) {
+        float t = 0.0f;
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        atomicAdd(&dst[c], t);
+    }
+}
+
+int launch_colsum_acc(int M, int N, const float *src, float *dst, cudaStream_t s)
+{
+    BDETR_REQUIRE(M > 0 && N > 0 && src && dst, BDETR_E_BAD_SHAPE, "bad colsum arguments");
+    const int rows_per_cta = 256;
+    dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_cta));
+    colsum_acc_kernel<<<grid, 256, 0, s>>>(M, N, src, dst, rows_per_cta);
+    BDETR_CHECK_LAUNCH("colsum_acc_kernel");
+    return BDETR_OK;
+}
+
+}  // namespace bdetr

@@ -1,0 +1,396 @@
+// Row-wise / column-wise fp32 kernels of the dense path: dropout + residual + LayerNorm (fwd/bwd),
+// positional add and its batch reduction, BatchNorm (+ReLU backward) and the prediction-head
+// activations with the boosted running sum.  All HBM-bound: coalesced float4 rows, warp shuffles.
+// Reference: transformers.py:139-151,182-193 (Dropout/Add/LayerNorm), :226-227,:441 (Add),
+// prediction_heads.py:59-62,126-129,196-199, boosted_model.py:222-229.
+#include <math_constants.h>
+#include "kernels.cuh"
+
+namespace bdetr {
+
+// ------------------------------------------------------------------------------------------
+// dropout + residual + LayerNorm.  One warp per row, NV float4 per lane (D = 128*NV).
+// ------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+res_ln_fwd_kernel(int M, const float *__restrict__ resid, float *__restrict__ z, const float *__restrict__ gamma,
+                  const float *__restrict__ beta, float eps, float keep_scale, uint32_t thresh, uint32_t key,
+                  float *__restrict__ out, float *__restrict__ mean_o, float *__restrict__ rstd_o)
+{
+    constexpr int D = NV * 128;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    float v[NV * 4];
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int col = (k * 32 + lane) * 4;
+        const size_t off = (size_t)row * D + col;
+        const float4 a = *reinterpret_cast<const float4 *>(z + off);
+        const float4 r = *reinterpret_cast<const float4 *>(resid + off);
+        float av[4] = {a.x, a.y, a.z, a.w};
+        const float rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (thresh) av[e] = dropout_keep((uint32_t)(off + e), key, thresh) ? av[e] * keep_scale : 0.0f;
+            v[4 * k + e] = rv[e] + av[e];
+            sum += v[4 * k + e];
+        }
+        *reinterpret_cast<float4 *>(z + off) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    }
+    const float mean = warp_sum(sum) * (1.0f / D);
+    float sq = 0.0f;
+#pragma unroll
+    for (int e = 0; e < NV * 4; ++e) { const float dlt = v[e] - mean; sq = fmaf(dlt, dlt, sq); }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int col = (k * 32 + lane) * 4;
+        const float4 g = *reinterpret_cast<const float4 *>(gamma + col);
+        const float4 bt = *reinterpret_cast<const float4 *>(beta + col);
+        float4 y;
+        y.x = (v[4 * k] - mean) * rstd * g.x + bt.x; y.y = (v[4 * k + 1] - mean) * rstd * g.y + bt.y;
+        y.z = (v[4 * k + 2] - mean) * rstd * g.z + bt.z; y.w = (v[4 * k + 3] - mean) * rstd * g.w + bt.w;
+        *reinterpret_cast<float4 *>(out + (size_t)row * D + col) = y;
+    }
+    if (lane == 0) { mean_o[row] = mean; rstd_o[row] = rstd; }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+res_ln_bwd_kernel(int M, const float *__restrict__ d_out, const float *__restrict__ z, const float *__restrict__ mean_i,
+                  const float *__restrict__ rstd_i, const float *__restrict__ gamma, float keep_scale, uint32_t thresh,
+                  uint32_t key, float *__restrict__ d_resid, int acc_resid, float *__restrict__ d_a,
+                  float *__restrict__ g_gamma, float *__restrict__ g_beta)
+{
+    constexpr int D = NV * 128;
+    __shared__ float red_g[8][D + 4];
+    __shared__ float red_b[8][D + 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    float gg[NV * 4], gb[NV * 4], gam[NV * 4];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const float4 g = *reinterpret_cast<const float4 *>(gamma + (k * 32 + lane) * 4);
+        gam[4 * k] = g.x; gam[4 * k + 1] = g.y; gam[4 * k + 2] = g.z; gam[4 * k + 3] = g.w;
+    }
+#pragma unroll
+    for (int e = 0; e < NV * 4; ++e) { gg[e] = 0.0f; gb[e] = 0.0f; }
+    for (int row = blockIdx.x * nwarp + warp; row < M; row += gridDim.x * nwarp) {
+        const float mean = mean_i[row], rstd = rstd_i[row];
+        float xh[NV * 4], dy[NV * 4];
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const size_t off = (size_t)row * D + (k * 32 + lane) * 4;
+            const float4 zz = *reinterpret_cast<const float4 *>(z + off);
+            const float4 dd = *reinterpret_cast<const float4 *>(d_out + off);
+            const float zv[4] = {zz.x, zz.y, zz.z, zz.w}, dv[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int idx = 4 * k + e;
+                xh[idx] = (zv[e] - mean) * rstd;
+                gg[idx] = fmaf(dv[e], xh[idx], gg[idx]);
+                gb[idx] += dv[e];
+                dy[idx] = dv[e] * gam[idx];           // d xhat
+                s1 += dy[idx];
+                s2 = fmaf(dy[idx], xh[idx], s2);
+            }
+        }
+        s1 = warp_sum(s1) * (1.0f / D);
+        s2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const size_t off = (size_t)row * D + (k * 32 + lane) * 4;
+            float dz[4], da[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int idx = 4 * k + e;
+                dz[e] = rstd * (dy[idx] - s1 - xh[idx] * s2);
+                da[e] = thresh ? (dropout_keep((uint32_t)(off + e), key, thresh) ? dz[e] * keep_scale : 0.0f) : dz[e];
+            }
+            *reinterpret_cast<float4 *>(d_a + off) = make_float4(da[0], da[1], da[2], da[3]);
+            if (d_resid) {
+                float4 r = make_float4(dz[0], dz[1], dz[2], dz[3]);
+                if (acc_resid) { const float4 c = *reinterpret_cast<const float4 *>(d_resid + off); r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w; }
+                *reinterpret_cast<float4 *>(d_resid + off) = r;
+            }
+        }
+    }
+    // reduce gamma/beta partials over the CTA's warps, one atomic per column per CTA
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            red_g[warp][(k * 32 + lane) * 4 + e] = gg[4 * k + e];
+            red_b[warp][(k * 32 + lane) * 4 + e] = gb[4 * k + e];
+        }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float a = 0.0f, b = 0.0f;
+        for (int w = 0; w < nwarp; ++w) { a += red_g[w][c]; b += red_b[w][c]; }
+        atomicAdd(&g_gamma[c], a);
+        atomicAdd(&g_beta[c], b);
+    }
+}
+
+int launch_res_ln_fwd(int M, int D, const float *resid, float *z, const float *gamma, const float *beta, float eps,
+                      float rate, uint32_t key, float *out, float *mean, float *rstd, cudaStream_t s)
+{
+    BDETR_REQUIRE(M > 0 && (D == 128 || D == 256 || D == 512), BDETR_E_UNSUPPORTED, "LayerNorm width must be 128, 256 or 512");
+    const uint32_t thresh = dropout_threshold(rate);
+    const float ks = 1.0f / (1.0f - rate);
+    const int grid = ceil_div(M, 8);
+    if (D == 128) res_ln_fwd_kernel<1><<<grid, 256, 0, s>>>(M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd);
+    else if (D == 256) res_ln_fwd_kernel<2><<<grid, 256, 0, s>>>(M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd);
+    else res_ln_fwd_kernel<4><<<grid, 256, 0, s>>>(M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd);
+    BDETR_CHECK_LAUNCH("res_ln_fwd_kernel");
+    return BDETR_OK;
+}
+
+int launch_res_ln_bwd(int M, int D, const float *d_out, const float *z, const float *mean, const float *rstd,
+                      const float *gamma, float rate, uint32_t key, float *d_resid, int acc_resid, float *d_a,
+                      float *g_gamma, float *g_beta, cudaStream_t s)
+{
+    BDETR_REQUIRE(M > 0 && (D == 128 || D == 256 || D == 512), BDETR_E_UNSUPPORTED, "LayerNorm width must be 128, 256 or 512");
+    const uint32_t thresh = dropout_threshold(rate);
+    const float ks = 1.0f / (1.0f - rate);
+    const int grid = min(ceil_div(M, 8), 296);
+    if (D == 128) res_ln_bwd_kernel<1><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta);
+    else if (D == 256) res_ln_bwd_kernel<2><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta);
+    else res_ln_bwd_kernel<4><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta);
+    BDETR_CHECK_LAUNCH("res_ln_bwd_kernel");
+    return BDETR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// elementwise helpers
+// ------------------------------------------------------------------------------------------
+__global__ void add_rows_fwd_kernel(size_t n4, size_t ld4, const float4 *__restrict__ x, const float4 *__restrict__ pos, float4 *__restrict__ out)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = x[e], p = pos[e % ld4];
+        out[e] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    }
+}
+__global__ void batch_sum_acc_kernel(int B, size_t ld4, const float4 *__restrict__ src, float4 *__restrict__ dst)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < ld4; e += (size_t)gridDim.x * blockDim.x) {
+        float4 a = dst[e];
+        for (int b = 0; b < B; ++b) { const float4 v = src[(size_t)b * ld4 + e]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+        dst[e] = a;
+    }
+}
+__global__ void tile_rows_kernel(size_t n4, size_t ld4, const float4 *__restrict__ src, float4 *__restrict__ dst)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) dst[e] = src[e % ld4];
+}
+__global__ void accumulate_kernel(size_t n, const float *__restrict__ x, float *__restrict__ y)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) y[e] += x[e];
+}
+
+static inline int ew_grid(size_t n) { size_t g = (n + 255) / 256; return (int)(g < 148 * 8 ? (g ? g : 1) : 148 * 8); }
+
+int launch_add_rows_fwd(int B, int L, int D, const float *x, const float *pos, float *out, cudaStream_t s)
+{
+    BDETR_REQUIRE(B > 0 && L > 0 && D > 0 && D % 4 == 0, BDETR_E_BAD_SHAPE, "D must be a multiple of 4");
+    const size_t ld4 = (size_t)L * D / 4, n4 = ld4 * B;
+    add_rows_fwd_kernel<<<ew_grid(n4), 256, 0, s>>>(n4, ld4, (const float4 *)x, (const float4 *)pos, (float4 *)out);
+    BDETR_CHECK_LAUNCH("add_rows_fwd_kernel");
+    return BDETR_OK;
+}
+int launch_batch_sum_acc(int B, int L, int D, const float *src, float *dst, cudaStream_t s)
+{
+    BDETR_REQUIRE(B > 0 && L > 0 && D > 0 && D % 4 == 0, BDETR_E_BAD_SHAPE, "D must be a multiple of 4");
+    const size_t ld4 = (size_t)L * D / 4;
+    batch_sum_acc_kernel<<<ew_grid(ld4), 256, 0, s>>>(B, ld4, (const float4 *)src, (float4 *)dst);
+    BDETR_CHECK_LAUNCH("batch_sum_acc_kernel");
+    return BDETR_OK;
+}
+int launch_tile_rows(int B, int L, int D, const float *src, float *dst, cudaStream_t s)
+{
+    BDETR_REQUIRE(B > 0 && L > 0 && D > 0 && D % 4 == 0, BDETR_E_BAD_SHAPE, "D must be a multiple of 4");
+    const size_t ld4 = (size_t)L * D / 4, n4 = ld4 * B;
+    tile_rows_kernel<<<ew_grid(n4), 256, 0, s>>>(n4, ld4, (const float4 *)src, (float4 *)dst);
+    BDETR_CHECK_LAUNCH("tile_rows_kernel");
+    return BDETR_OK;
+}
+int launch_accumulate(size_t n, const float *x, float *y, cudaStream_t s)
+{
+    BDETR_REQUIRE(n > 0 && x && y, BDETR_E_BAD_SHAPE, "bad accumulate arguments");
+    accumulate_kernel<<<ew_grid(n), 256, 0, s>>>(n, x, y);
+    BDETR_CHECK_LAUNCH("accumulate_kernel");
+    return BDETR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm over the rows of [M, Dh] (Keras non-fused path: biased variance, eps inside rsqrt).
+// CTA = 32 columns x 8 row-lanes.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float col_reduce8(float v, float (*red)[33])
+{
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    __syncthreads();
+    red[r][c] = v;
+    __syncthreads();
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][c];
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+bn_fwd_kernel(int M, int Dh, const float *__restrict__ h, const float *__restrict__ gamma, const float *__restrict__ beta,
+              float *__restrict__ moving_mean, float *__restrict__ moving_var, float eps, float momentum, int training,
+              float *__restrict__ hn, float *__restrict__ mean_o, float *__restrict__ rstd_o)
+{
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+    const bool live = c < Dh;
+    float mean, var;
+    if (training) {
+        float s = 0.0f;
+        if (live) for (int m = r; m < M; m += 8) s += h[(size_t)m * Dh + c];
+        mean = col_reduce8(s, red) / (float)M;
+        float q = 0.0f;
+        if (live) for (int m = r; m < M; m += 8) { const float d = h[(size_t)m * Dh + c] - mean; q = fmaf(d, d, q); }
+        var = col_reduce8(q, red) / (float)M;
+        if (live && r == 0) {
+            moving_mean[c] = moving_mean[c] * momentum + mean * (1.0f - momentum);
+            moving_var[c] = moving_var[c] * momentum + var * (1.0f - momentum);
+        }
+    } else {
+        mean = live ? moving_mean[c] : 0.0f;
+        var = live ? moving_var[c] : 1.0f;
+    }
+    const float rstd = rsqrtf(var + eps);
+    if (!live) return;
+    if (r == 0) { mean_o[c] = mean; rstd_o[c] = rstd; }
+    const float g = gamma[c], b = beta[c];
+    for (int m = r; m < M; m += 8) hn[(size_t)m * Dh + c] = (h[(size_t)m * Dh + c] - mean) * rstd * g + b;
+}
+
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_kernel(int M, int Dh, const float *__restrict__ h, const float *__restrict__ d_hn, const float *__restrict__ gamma,
+                   const float *__restrict__ mean_i, const float *__restrict__ rstd_i, float *__restrict__ d_h,
+                   float *__restrict__ g_gamma, float *__restrict__ g_beta)
+{
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+    const bool live = c < Dh;
+    const float mean = live ? mean_i[c] : 0.0f, rstd = live ? rstd_i[c] : 0.0f, g = live ? gamma[c] : 0.0f;
+    float s1 = 0.0f, s2 = 0.0f;
+    if (live) for (int m = r; m < M; m += 8) {
+        const float dy = d_hn[(size_t)m * Dh + c];
+        s1 += dy;
+        s2 = fmaf(dy, (h[(size_t)m * Dh + c] - mean) * rstd, s2);
+    }
+    s1 = col_reduce8(s1, red);      // sum dy        (= d beta)
+    s2 = col_reduce8(s2, red);      // sum dy * xhat (= d gamma)
+    if (!live) return;
+    if (r == 0) { g_gamma[c] += s2; g_beta[c] += s1; }
+    const float invM = 1.0f / (float)M;
+    for (int m = r; m < M; m += 8) {
+        const size_t off = (size_t)m * Dh + c;
+        const float hv = h[off];
+        const float xh = (hv - mean) * rstd;
+        const float dx = g * rstd * (d_hn[off] - s1 * invM - xh * s2 * invM);
+        d_h[off] = hv > 0.0f ? dx : 0.0f;           // ReLU backward (h is the post-ReLU activation)
+    }
+}
+
+int launch_bn_fwd(int M, int Dh, const float *h, const float *gamma, const float *beta, float *moving_mean,
+                  float *moving_var, float eps, float momentum, int training, float *hn, float *mean, float *rstd,
+                  cudaStream_t s)
+{
+    BDETR_REQUIRE(M > 0 && Dh > 0, BDETR_E_BAD_SHAPE, "bad BatchNorm shape");
+    bn_fwd_kernel<<<ceil_div(Dh, 32), 256, 0, s>>>(M, Dh, h, gamma, beta, moving_mean, moving_var, eps, momentum, training, hn, mean, rstd);
+    BDETR_CHECK_LAUNCH("bn_fwd_kernel");
+    return BDETR_OK;
+}
+int launch_bn_relu_bwd(int M, int Dh, const float *h, const float *d_hn, const float *gamma, const float *mean,
+                       const float *rstd, float *d_h, float *g_gamma, float *g_beta, cudaStream_t s)
+{
+    BDETR_REQUIRE(M > 0 && Dh > 0, BDETR_E_BAD_SHAPE, "bad BatchNorm shape");
+    bn_relu_bwd_kernel<<<ceil_div(Dh, 32), 256, 0, s>>>(M, Dh, h, d_hn, gamma, mean, rstd, d_h, g_gamma, g_beta);
+    BDETR_CHECK_LAUNCH("bn_relu_bwd_kernel");
+    return BDETR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// head activations + boosted running sum.  One warp per row.
+// kind 0: softmax, 1: sigmoid, 2: 3*sigmoid(x/100) - 1
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(256)
+head_act_fwd_kernel(int M, int N, int kind, float mult, float *__restrict__ act, float *__restrict__ cum, int cum_init)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    float *a = act + (size_t)row * N;
+    float *c = cum + (size_t)row * N;
+    if (kind == 0) {
+        float mx = -CUDART_INF_F;
+        for (int n = lane; n < N; n += 32) mx = fmaxf(mx, a[n]);
+        mx = warp_max(mx);
+        float s = 0.0f;
+        for (int n = lane; n < N; n += 32) s += expf(a[n] - mx);
+        s = warp_sum(s);
+        for (int n = lane; n < N; n += 32) {
+            const float p = expf(a[n] - mx) / s;
+            a[n] = p;
+            c[n] = (cum_init ? 0.0f : c[n]) + mult * p;
+        }
+    } else {
+        for (int n = lane; n < N; n += 32) {
+            const float v = kind == 1 ? sigmoidf_(a[n]) : 3.0f * sigmoidf_(a[n] / 100.0f) - 1.0f;
+            a[n] = v;
+            c[n] = (cum_init ? 0.0f : c[n]) + mult * v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+head_act_bwd_kernel(int M, int N, int kind, float mult, const float *__restrict__ act, const float *__restrict__ d_cum,
+                    float *__restrict__ d_logits)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float *a = act + (size_t)row * N;
+    const float *g = d_cum + (size_t)row * N;
+    float *d = d_logits + (size_t)row * N;
+    if (kind == 0) {
+        float dot = 0.0f;
+        for (int n = lane; n < N; n += 32) dot = fmaf(g[n], a[n], dot);
+        dot = warp_sum(dot);
+        for (int n = lane; n < N; n += 32) d[n] = mult * a[n] * (g[n] - dot);
+    } else if (kind == 1) {
+        for (int n = lane; n < N; n += 32) d[n] = mult * g[n] * a[n] * (1.0f - a[n]);
+    } else {
+        for (int n = lane; n < N; n += 32) {
+            const float sg = (a[n] + 1.0f) / 3.0f;
+            d[n] = mult * g[n] * 3.0f * sg * (1.0f - sg) / 100.0f;
+        }
+    }
+}
+
+int launch_head_act_fwd(int M, int N, int kind, float mult, float *act, float *cum, int cum_init, cudaStream_t s)
+{
+    BDETR_REQUIRE(M > 0 && N > 0 && kind >= 0 && kind <= 2, BDETR_E_BAD_SHAPE, "bad head activation arguments");
+    head_act_fwd_kernel<<<ceil_div(M, 8), 256, 0, s>>>(M, N, kind, mult, act, cum, cum_init);
+    BDETR_CHECK_LAUNCH("head_act_fwd_kernel");
+    return BDETR_OK;
+}
+int launch_head_act_bwd(int M, int N, int kind, float mult, const float *act, const float *d_cum, float *d_logits, cudaStream_t s)
+{
+    BDETR_REQUIRE(M > 0 && N > 0 && kind >= 0 && kind <= 2, BDETR_E_BAD_SHAPE, "bad head activation arguments");
+    head_act_bwd_kernel<<<ceil_div(M, 8), 256, 0, s>>>(M, N, kind, mult, act, d_cum, d_logits);
+    BDETR_CHECK_LAUNCH("head_act_bwd_kernel");
+    return BDETR_OK;
+}
+
+}  // namespace bdetr

@@ -1,0 +1,368 @@
+"""Boosted encoder / decoder transformer layers — same class names, constructor arguments and call
+conventions as the reference's ModelComponents/transformers.py, executed by libbdetr.so."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device import empty, f32, ptr, stream_ptr
+from .layers import Layer, glorot_normal
+
+DROPOUT_RATE = 0.1   # reference transformers.py:135,179
+LN_EPS = 1e-3        # reference :137 (explicit) / Keras default (:180)
+
+
+def _struct(cls, tensors: dict):
+    s = cls()
+    for k, _ in cls._fields_:
+        t = tensors.get(k)
+        setattr(s, k, None if t is None else t.data_ptr())
+    return s
+
+
+class MultiheadAttention(Layer):
+    """Weight holder for the four Dense projections (reference :18-109).  The computation runs inside
+    AttentionBlock's fused entry point; heads are column slices, and the [B,H,Lq,d] output is re-read
+    as [B,Lq,H*d] without a permute, exactly like reference line :100."""
+
+    def __init__(self, num_attention_heads, dim, name="MultiheadAttention", **kwargs):
+        super().__init__(name=name)
+        self.num_attention_heads = num_attention_heads
+        self.dim = dim
+
+    def get_config(self):
+        return {**super().get_config(), "num_attention_heads": self.num_attention_heads, "dim": self.dim}
+
+    def build(self, input_shape):
+        query_dim = input_shape[0][-1]
+        proj = self.num_attention_heads * self.dim
+        rng = Layer._rng
+        for nm, (fi, fo) in {"QueryProjection": (input_shape[0][-1], proj), "KeyProjection": (input_shape[1][-1], proj),
+                             "ValueProjection": (input_shape[2][-1], proj), "OutputProjection": (proj, query_dim)}.items():
+            self.add_weight(f"{nm}/kernel", glorot_normal(rng, fi, fo))
+            self.add_weight(f"{nm}/bias", np.zeros(fo, np.float32))
+
+    def forward(self, inputs, training=False):
+        raise NotImplementedError("MultiheadAttention runs fused inside AttentionBlock (bdetr_attention_block_fwd)")
+
+
+class AttentionBlock(Layer):
+    """LayerNorm(query + Dropout(MHA(query, key, value)))  (reference :112-158)."""
+
+    def __init__(self, num_attention_heads, name="AttentionBlock", **kwargs):
+        super().__init__(name=name)
+        self.num_attention_heads = num_attention_heads
+        self.AttentionLayer = None
+        self.rate = DROPOUT_RATE
+
+    def get_config(self):
+        return {**super().get_config(), "num_attention_heads": self.num_attention_heads}
+
+    def build(self, input_shape):
+        D = input_shape[0][-1]
+        assert D % self.num_attention_heads == 0
+        self.AttentionLayer = MultiheadAttention(self.num_attention_heads, D // self.num_attention_heads, name="AttentionLayer")
+        self.AttentionLayer.build(input_shape)
+        self.AttentionLayer.built = True
+        self.add_weight("LayerNorm/gamma", np.ones(D, np.float32))
+        self.add_weight("LayerNorm/beta", np.zeros(D, np.float32))
+
+    def _structs(self):
+        if self._struct_cache is None:
+            a = self.AttentionLayer
+            def pack(src_a, src_s):
+                return _struct(_lib.AttnParams, {
+                    "wq": src_a["QueryProjection/kernel"], "bq": src_a["QueryProjection/bias"],
+                    "wk": src_a["KeyProjection/kernel"], "bk": src_a["KeyProjection/bias"],
+                    "wv": src_a["ValueProjection/kernel"], "bv": src_a["ValueProjection/bias"],
+                    "wo": src_a["OutputProjection/kernel"], "bo": src_a["OutputProjection/bias"],
+                    "ln_gamma": src_s["LayerNorm/gamma"], "ln_beta": src_s["LayerNorm/beta"]})
+            self._struct_cache = (pack(a._weights, self._weights), pack(a._grads, self._grads))
+        return self._struct_cache
+
+    def forward(self, inputs, training=False, dropout_key=0):
+        query, key, value = (f32(t) for t in inputs)
+        self.maybe_build([query, key, value])
+        B, Lq, D = query.shape
+        Lk, H = key.shape[1], self.num_attention_heads
+        sv = {"qp": empty(B, Lq, D), "kp": empty(B, Lk, D), "vp": empty(B, Lk, D), "o": empty(B, H, Lq, D // H),
+              "lse": empty(B, H, Lq), "z": empty(B, Lq, D), "mean": empty(B * Lq), "rstd": empty(B * Lq)}
+        out = empty(B, Lq, D)
+        rate = self.rate if training else 0.0
+        w, _ = self._structs()
+        svs = _struct(_lib.AttnSaved, sv)
+        _lib.call("bdetr_attention_block_fwd", B, Lq, Lk, D, H, ptr(query), ptr(key), ptr(value), ctypes.byref(w),
+                  rate, dropout_key, LN_EPS, ptr(out), ctypes.byref(svs), stream_ptr())
+        ctx = {"inputs": (query, key, value), "saved": sv, "saved_struct": svs, "rate": rate, "key": dropout_key,
+               "dims": (B, Lq, Lk, D, H)}
+        return out, ctx
+
+    def backward(self, ctx, d_out, d_query=None, d_key=None, d_value=None, acc=(False, False, False)):
+        """Returns (d_query, d_key, d_value); parameter gradients are accumulated into self._grads.
+        Pass existing buffers (+acc flags) to accumulate into them.  query-is-key inputs share one buffer."""
+        query, key, value = ctx["inputs"]
+        B, Lq, Lk, D, H = ctx["dims"]
+        acc = list(acc)
+        if d_query is None:
+            d_query, acc[0] = empty(B, Lq, D), False
+        if d_key is None:
+            if key is query:
+                d_key, acc[1] = d_query, True
+            else:
+                d_key, acc[1] = empty(B, Lk, D), False
+        if d_value is None:
+            if value is query:
+                d_value, acc[2] = d_query, True
+            elif value is key:
+                d_value, acc[2] = d_key, True
+            else:
+                d_value, acc[2] = empty(B, Lk, D), False
+        sc = {"d_qp": empty(B, Lq, D), "d_kp": empty(B, Lk, D), "d_vp": empty(B, Lk, D), "d_o": empty(B, H, Lq, D // H),
+              "d_z": empty(B, Lq, D), "delta": empty(B, H, Lq)}
+        w, gw = self._structs()
+        scs = _struct(_lib.AttnScratch, sc)
+        flags = (1 if acc[0] else 0) | (2 if acc[1] else 0) | (4 if acc[2] else 0)
+        _lib.call("bdetr_attention_block_bwd", B, Lq, Lk, D, H, ptr(query), ptr(key), ptr(value), ctypes.byref(w),
+                  ctx["rate"], ctx["key"], ctypes.byref(ctx["saved_struct"]), ptr(f32(d_out)),
+                  ptr(d_query), ptr(d_key), ptr(d_value), flags, ctypes.byref(gw), ctypes.byref(scs), stream_ptr())
+        return d_query, d_key, d_value
+
+
+class FeedForwardBlock(Layer):
+    """LayerNorm(x + Dropout(DenseLinear(DenseRelu(x))))  (reference :161-198); hidden width = feature dim."""
+
+    def __init__(self, name="FeedForwardBlock", **kwargs):
+        super().__init__(name=name)
+        self.rate = DROPOUT_RATE
+
+    def build(self, input_shape):
+        D = input_shape[0][-1]
+        rng = Layer._rng
+        self.add_weight("DenseRelu/kernel", glorot_normal(rng, D, D))
+        self.add_weight("DenseRelu/bias", np.zeros(D, np.float32))
+        self.add_weight("DenseLinear/kernel", glorot_normal(rng, D, D))
+        self.add_weight("DenseLinear/bias", np.zeros(D, np.float32))
+        self.add_weight("LayerNorm/gamma", np.ones(D, np.float32))
+        self.add_weight("LayerNorm/beta", np.zeros(D, np.float32))
+
+    def _structs(self):
+        if self._struct_cache is None:
+            pack = lambda s: _struct(_lib.FfnParams, {"w1": s["DenseRelu/kernel"], "b1": s["DenseRelu/bias"],
+                                                      "w2": s["DenseLinear/kernel"], "b2": s["DenseLinear/bias"],
+                                                      "ln_gamma": s["LayerNorm/gamma"], "ln_beta": s["LayerNorm/beta"]})
+            self._struct_cache = (pack(self._weights), pack(self._grads))
+        return self._struct_cache
+
+    def forward(self, inputs, training=False, dropout_key=0):
+        x = f32(inputs[0])
+        self.maybe_build([x])
+        D = x.shape[-1]
+        M = x.numel() // D
+        sv = {"h": empty(M, D), "z": empty(M, D), "mean": empty(M), "rstd": empty(M)}
+        out = torch.empty_like(x)
+        rate = self.rate if training else 0.0
+        w, _ = self._structs()
+        svs = _struct(_lib.FfnSaved, sv)
+        _lib.call("bdetr_ffn_block_fwd", M, D, ptr(x), ctypes.byref(w), rate, dropout_key, LN_EPS, ptr(out),
+                  ctypes.byref(svs), stream_ptr())
+        return out, {"x": x, "saved": sv, "saved_struct": svs, "rate": rate, "key": dropout_key, "dims": (M, D)}
+
+    def backward(self, ctx, d_out, d_x=None, acc=False):
+        M, D = ctx["dims"]
+        if d_x is None:
+            d_x, acc = torch.empty_like(ctx["x"]), False
+        sc = {"d_z": empty(M, D), "d_h": empty(M, D)}
+        w, gw = self._structs()
+        scs = _struct(_lib.FfnScratch, sc)
+        _lib.call("bdetr_ffn_block_bwd", M, D, ptr(ctx["x"]), ctypes.byref(w), ctx["rate"], ctx["key"],
+                  ctypes.byref(ctx["saved_struct"]), ptr(f32(d_out)), ptr(d_x), 1 if acc else 0, ctypes.byref(gw),
+                  ctypes.byref(scs), stream_ptr())
+        return d_x
+
+
+def add_positional(x, pos):
+    B, L, D = x.shape
+    out = torch.empty_like(x)
+    _lib.call("bdetr_add_positional_fwd", B, L, D, ptr(x), ptr(pos), ptr(out), stream_ptr())
+    return out
+
+
+def batch_sum_into(d_out, d_param):
+    B, L, D = d_out.shape
+    _lib.call("bdetr_add_positional_bwd", B, L, D, ptr(d_out), ptr(d_param), stream_ptr())
+
+
+def accumulate(x, y):
+    _lib.call("bdetr_accumulate", x.numel(), ptr(x), ptr(y), stream_ptr())
+
+
+class EncoderBlock(Layer):
+    """q = k = x + pos, v = x -> AttentionBlock -> FeedForwardBlock  (reference :200-241).
+    `encoder_positional` is the un-tiled [L,D] table (batch-invariant; the reference tiles it)."""
+
+    def __init__(self, num_attention_heads, name="EncoderBlock", **kwargs):
+        super().__init__(name=name)
+        self.num_attention_heads = num_attention_heads
+        self.SelfAttentionBlock = AttentionBlock(num_attention_heads, name="SelfAttentionBlock")
+        self.FeedForwardBlock = FeedForwardBlock(name="FeedForwardBlock")
+
+    def get_config(self):
+        return {**super().get_config(), "num_attention_heads": self.num_attention_heads}
+
+    def forward(self, inputs, training=False, dropout_keys=(0, 0)):
+        x, pos = inputs
+        x = f32(x)
+        xp = add_positional(x, pos)                                   # Add1 == Add2 (:226-227)
+        a, c1 = self.SelfAttentionBlock.forward([xp, xp, x], training, dropout_keys[0])
+        y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[1])
+        return y, {"attn": c1, "ffn": c2}
+
+    def backward(self, ctx, d_out, d_pos):
+        """Returns d_x; accumulates the positional gradient (summed over the batch) into d_pos."""
+        d_a = self.FeedForwardBlock.backward(ctx["ffn"], d_out)
+        d_xp, _, d_x = self.SelfAttentionBlock.backward(ctx["attn"], d_a)   # d_key aliases d_query (same tensor)
+        batch_sum_into(d_xp, d_pos)
+        accumulate(d_xp, d_x)
+        return d_x
+
+
+def positional_table(rows, cols, dim):
+    """Sine/cosine initial value of the trainable table (reference :282-291): odd flattened position ->
+    sin, even -> cos, denominator 2(1+dim)/D.  Vectorised (the reference uses a Python double loop)."""
+    k = np.arange(rows * cols, dtype=np.float64)[:, None]
+    den = 2.0 * (1.0 + np.arange(dim, dtype=np.float64))[None, :] / dim
+    tab = np.where((k % 2) == 1, np.sin(k / den), np.cos(k / den))
+    return tab.reshape(rows, cols, dim).astype(np.float32)
+
+
+class ImageEncoderAttention(Layer):
+    """call([x4d]) -> (x4d, positional4d)  (reference :244-321).  The returned positional encoding is
+    the [rows, cols, D] table itself (not tiled over the batch; DecoderPrep accepts both)."""
+
+    def __init__(self, num_blocks, num_attention_heads, name="ImageEncoderAttention", **kwargs):
+        super().__init__(name=name)
+        self.num_blocks = num_blocks
+        self.num_attention_heads = num_attention_heads
+        self.EncoderBlocks = [EncoderBlock(num_attention_heads, name=f"EncoderBlock_{i}") for i in range(num_blocks)]
+
+    def get_config(self):
+        return {**super().get_config(), "num_blocks": self.num_blocks, "num_attention_heads": self.num_attention_heads}
+
+    def build(self, input_shape):
+        _, R, Cc, D = input_shape[0]
+        self.add_weight("positional_encoding", positional_table(R, Cc, D))
+
+    def forward(self, inputs, training=False, dropout_keys=None):
+        x4 = f32(inputs[0])
+        self.maybe_build([x4])
+        B, R, Cc, D = x4.shape
+        pos = self._weights["positional_encoding"]
+        x = x4.view(B, R * Cc, D)
+        ctxs = []
+        for i, blk in enumerate(self.EncoderBlocks):
+            keys = (0, 0) if dropout_keys is None else dropout_keys[i]
+            x, c = blk.forward([x, pos.view(R * Cc, D)], training, keys)
+            ctxs.append(c)
+        return (x.view(B, R, Cc, D), pos), {"blocks": ctxs, "shape": (B, R, Cc, D)}
+
+    def backward(self, ctx, d_x4, d_pos_extra=None):
+        """d_x4: gradient of the encoder output; d_pos_extra: gradient arriving at the returned table."""
+        B, R, Cc, D = ctx["shape"]
+        g_pos = self._grads["positional_encoding"].view(R * Cc, D)
+        if d_pos_extra is not None:
+            accumulate(d_pos_extra.reshape(R * Cc, D), g_pos)
+        d = d_x4.view(B, R * Cc, D)
+        for blk, c in zip(reversed(self.EncoderBlocks), reversed(ctx["blocks"])):
+            d = blk.backward(c, d, g_pos)
+        return d.view(B, R, Cc, D)
+
+
+class DecoderPrep(Layer):
+    """call([x4d, pos]) -> (encoder_value, decoder_features, encoder_key, decoder_positional)  (reference :397-456)."""
+
+    def __init__(self, num_object_preds, decoder_dim, name="DecoderPrep", **kwargs):
+        super().__init__(name=name)
+        self.num_object_preds = num_object_preds
+        self.decoder_dim = decoder_dim
+
+    def get_config(self):
+        return {**super().get_config(), "num_object_preds": self.num_object_preds, "decoder_dim": self.decoder_dim}
+
+    def build(self, input_shape):
+        # zeros initialiser, trainable (reference :427-431)
+        self.add_weight("init_decoder_features", np.zeros((self.num_object_preds, self.decoder_dim), np.float32))
+
+    def forward(self, inputs, training=False):
+        x4, pos = inputs
+        x4 = f32(x4)
+        self.maybe_build([x4])
+        B, R, Cc, D = x4.shape
+        enc_value = x4.view(B, R * Cc, D)
+        enc_key = add_positional(enc_value, pos.reshape(-1, D)[: R * Cc])      # Add (:441)
+        q0 = self._weights["init_decoder_features"]
+        dec = empty(B, *q0.shape)
+        _lib.call("bdetr_tile_queries_fwd", B, q0.shape[0], q0.shape[1], ptr(q0), ptr(dec), stream_ptr())
+        return (enc_value, dec, enc_key, dec), {"shape": (B, R, Cc, D)}
+
+    def backward(self, ctx, d_enc_value, d_dec, d_enc_key, d_pos):
+        """Returns d_x4; accumulates into d_pos ([L,D]) and into the query parameter's gradient."""
+        B, R, Cc, D = ctx["shape"]
+        batch_sum_into(d_dec, self._grads["init_decoder_features"])
+        batch_sum_into(d_enc_key, d_pos)
+        accumulate(d_enc_key, d_enc_value)
+        return d_enc_value.view(B, R, Cc, D)
+
+
+class DecoderBlock_NoSelfAttention(Layer):
+    """cross-attention -> FFN  (reference :324-353)."""
+
+    def __init__(self, num_attention_heads, name="DecoderBlock_NoSelfAttention", **kwargs):
+        super().__init__(name=name)
+        self.num_attention_heads = num_attention_heads
+        self.JointAttentionBlock = AttentionBlock(num_attention_heads, name="JointAttentionBlock")
+        self.FeedForwardBlock = FeedForwardBlock(name="FeedForwardBlock")
+
+    def get_config(self):
+        return {**super().get_config(), "num_attention_heads": self.num_attention_heads}
+
+    def forward(self, inputs, training=False, dropout_keys=(0, 0, 0)):
+        enc_value, dec, enc_key, _ = inputs
+        a, c1 = self.JointAttentionBlock.forward([dec, enc_key, enc_value], training, dropout_keys[1])
+        y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[2])
+        return y, {"joint": c1, "ffn": c2}
+
+    def backward(self, ctx, d_out):
+        """Returns (d_enc_value, d_dec, d_enc_key)."""
+        d_a = self.FeedForwardBlock.backward(ctx["ffn"], d_out)
+        d_dec, d_key, d_val = self.JointAttentionBlock.backward(ctx["joint"], d_a)
+        return d_val, d_dec, d_key
+
+
+class DecoderBlock(Layer):
+    """self-attention (no positional, reference :378-380) -> cross-attention -> FFN  (reference :356-394)."""
+
+    def __init__(self, num_attention_heads, name="DecoderBlock", **kwargs):
+        super().__init__(name=name)
+        self.num_attention_heads = num_attention_heads
+        self.SelfAttentionBlock = AttentionBlock(num_attention_heads, name="SelfAttentionBlock")
+        self.JointAttentionBlock = AttentionBlock(num_attention_heads, name="JointAttentionBlock")
+        self.FeedForwardBlock = FeedForwardBlock(name="FeedForwardBlock")
+
+    def get_config(self):
+        return {**super().get_config(), "num_attention_heads": self.num_attention_heads}
+
+    def forward(self, inputs, training=False, dropout_keys=(0, 0, 0)):
+        enc_value, dec, enc_key, _ = inputs
+        s, c0 = self.SelfAttentionBlock.forward([dec, dec, dec], training, dropout_keys[0])
+        a, c1 = self.JointAttentionBlock.forward([s, enc_key, enc_value], training, dropout_keys[1])
+        y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[2])
+        return y, {"self": c0, "joint": c1, "ffn": c2}
+
+    def backward(self, ctx, d_out):
+        d_a = self.FeedForwardBlock.backward(ctx["ffn"], d_out)
+        d_s, d_key, d_val = self.JointAttentionBlock.backward(ctx["joint"], d_a)
+        d_dec, _, _ = self.SelfAttentionBlock.backward(ctx["self"], d_s)     # q = k = v share one buffer
+        return d_val, d_dec, d_key

@@ -60,7 +60,7 @@ def dropout_key(seed: int, site: int) -> int:
 def dropout_keep_mask(n: int, seed: int, site: int, rate: float = DROPOUT_RATE) -> np.ndarray:
     idx = np.arange(n, dtype=np.uint64)
     h = _lowbias32(idx ^ np.uint64(dropout_key(seed, site)))
-    thresh = np.uint64(int(rate * 4294967296.0))
+    thresh = np.uint64(int(float(np.float32(rate)) * 4294967296.0))   # the kernels take `rate` as fp32
     return h >= thresh
 
 
