@@ -139,10 +139,8 @@ class BoostedDETR:
                     o._grads[k].zero_()
 
     # -- inputs --------------------------------------------------------------------------------
-    def _to_device(self, name, x, dtype):
-        """numpy -> persistent pinned staging buffer -> HBM (async on the current stream)."""
-        if isinstance(x, torch.Tensor) and x.is_cuda:
-            return i32(x) if dtype == "i32" else f32(x)
+    def _pinned(self, name, x, dtype):
+        """numpy -> persistent pinned staging buffer (counted in self.h2d_bytes)."""
         arr = x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
         arr = np.ascontiguousarray(arr, dtype=np.int32 if dtype == "i32" else np.float32)
         stage = getattr(self, "_staging", None)
@@ -153,7 +151,13 @@ class BoostedDETR:
             stage[key] = torch.empty(arr.shape, dtype=torch.int32 if dtype == "i32" else torch.float32).pin_memory()
         stage[key].numpy()[...] = arr
         self.h2d_bytes += arr.nbytes
-        return stage[key].to(require_cuda(), non_blocking=True)
+        return stage[key]
+
+    def _to_device(self, name, x, dtype):
+        """host array -> pinned staging -> HBM (async on the current stream); CUDA tensors pass through."""
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            return i32(x) if dtype == "i32" else f32(x)
+        return self._pinned(name, x, dtype).to(require_cuda(), non_blocking=True)
 
     def _prepare(self, inputs, training):
         self.h2d_bytes = 0

@@ -575,12 +575,17 @@ extern "C" __attribute__((visibility("default"))) int bdetr_cost_matrix_fwd(int 
     const CostSmemLayout L = cost_smem_layout(T, C, A, has_attr);
     BDETR_REQUIRE(L.bytes <= 227 * 1024, BDETR_E_UNSUPPORTED, "C/A/T too large for the shared-memory tile");
     dim3 grid(ceil_div(Q, CM_QT), B);
+    // opt in to large dynamic shared memory once per size class (never during a later graph capture)
+    static size_t optin[2] = {0, 0};
+    if (L.bytes > optin[has_attr]) {
+        if (has_attr) BDETR_CUDA(cudaFuncSetAttribute(cost_matrix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
+        else BDETR_CUDA(cudaFuncSetAttribute(cost_matrix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
+        optin[has_attr] = L.bytes;
+    }
     if (has_attr) {
-        BDETR_CUDA(cudaFuncSetAttribute(cost_matrix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
         cost_matrix_kernel<true><<<grid, CM_THREADS, L.bytes, as_stream(stream)>>>(
             T, Q, C, A, cat_true, attr_true, box_true, cat_pred, attr_pred, box_pred, w_cat, w_box, w_attr, cost, L);
     } else {
-        BDETR_CUDA(cudaFuncSetAttribute(cost_matrix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
         cost_matrix_kernel<false><<<grid, CM_THREADS, L.bytes, as_stream(stream)>>>(
             T, Q, C, A, cat_true, attr_true, box_true, cat_pred, attr_pred, box_pred, w_cat, w_box, w_attr, cost, L);
     }
@@ -610,7 +615,11 @@ extern "C" __attribute__((visibility("default"))) int bdetr_lsap_assign(int B, i
         lsap_validate_kernel<<<blocks, 256, 0, s>>>(B, T, Q, cost, num_objects, status);
         BDETR_CHECK_LAUNCH("lsap_validate_kernel");
     }
-    BDETR_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t lsap_optin = 0;
+    if (smem > lsap_optin) {
+        BDETR_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lsap_optin = smem;
+    }
     lsap_kernel<<<B, 32, smem, s>>>(T, Q, cost, num_objects, col4row, row4col, status);
     BDETR_CHECK_LAUNCH("lsap_kernel");
     if (mask || assigned) {

@@ -1,0 +1,76 @@
+"""CUDA-graph replay of the training step: the whole fwd + matcher + bwd chain is ~600 small kernels, so at
+BASELINE config 2 the step is launch-bound; one graph launch replaces the Python/ctypes launch sequence."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .losses_and_metrics import raise_for_status
+
+
+class GraphedTrainStep:
+    """Captures model.forward + backward for fixed shapes.  __call__(inputs) copies the batch into the static
+    input buffers (H2D from pinned staging when given numpy), replays, and returns the metric tensors."""
+
+    def __init__(self, model, example_inputs, warmup=3):
+        self.model = model
+        if model._flat is None:
+            model.build()
+        self.static = {}
+        feats, y_true = model._prepare(example_inputs, True)
+        self.static = {"features": feats.clone(), "category": y_true[0].clone(), "attribute": y_true[1].clone(),
+                       "bbox": y_true[2].clone(), "num_objects": y_true[3].clone()}
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.static.values())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.metrics, self.status = self._step()
+        torch.cuda.synchronize()
+
+    def _step(self):
+        m = self.model
+        s = self.static
+        m.zero_grads()
+        y_true = [s["category"], s["attribute"], s["bbox"], s["num_objects"]]
+        _, ctx = m.forward(s["features"], y_true, True)
+        metrics = m._collect_metrics(ctx)
+        m.backward(ctx, gscale=1.0 / m.num_replicas)
+        status = torch.stack([c["status"] for c in ctx["loss"]])
+        return metrics, status
+
+    def load(self, inputs):
+        """Host batch -> (pinned staging) -> static device buffers, async on the current stream."""
+        m = self.model
+        m.h2d_bytes = 0
+        for k in ("features", "category", "attribute", "bbox", "num_objects"):
+            x, dst = inputs[k], self.static[k]
+            dtype = "i32" if k == "num_objects" else "f32"
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                if x.data_ptr() != dst.data_ptr():
+                    dst.copy_(x.reshape(dst.shape), non_blocking=True)
+            else:
+                dst.copy_(m._pinned(k, x, dtype).reshape(dst.shape), non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        m = self.model
+        if m.grad_allreduce is not None:
+            m.grad_allreduce(m._flat[1])
+        if m.optimizer is not None:
+            m.optimizer.apply(m)
+        m.step_count += 1
+
+    def __call__(self, inputs, return_host=True):
+        self.load(inputs)
+        self.replay()
+        if not return_host:
+            return self.metrics
+        out = {k: float(v.mean().item()) for k, v in self.metrics.items()}
+        raise_for_status(self.status.reshape(-1))
+        return out

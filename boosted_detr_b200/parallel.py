@@ -1,0 +1,62 @@
+"""Data-parallel plumbing: one process per GPU, torch.distributed (NCCL over NVLink) for the gradient
+all-reduce — the only collective on the path.  Per-replica BatchNorm statistics and loss
+normaliser, loss scaled by 1/replicas, gradients summed: the semantics of the reference's
+tf.distribute.MirroredStrategy (parameters.py:74)."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Reads RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* (torchrun).  Returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_batch(inputs: dict, rank: int, world: int) -> dict:
+    """Splits the global batch evenly by image (partitioning of SURVEY.md §8e)."""
+    out = {}
+    for k, v in inputs.items():
+        n = v.shape[0]
+        assert n % world == 0, "global batch must divide evenly across replicas"
+        per = n // world
+        out[k] = v[rank * per:(rank + 1) * per]
+    return out
+
+
+class DataParallel:
+    """Attaches the gradient all-reduce to a BoostedDETR: model.train_step then computes
+    sum over replicas of d(loss_replica / world)/d(theta)."""
+
+    def __init__(self, model, bucket_bytes=None):
+        self.model = model
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        model.num_replicas = self.world
+        if self.world > 1:
+            model.grad_allreduce = self.allreduce
+        self.broadcast_weights()
+
+    def allreduce(self, flat_grads: torch.Tensor):
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+
+    def broadcast_weights(self):
+        if self.world > 1:
+            if self.model._flat is None:
+                self.model.build()
+            dist.broadcast(self.model._flat[0], src=0)
+            for _, o, k in self.model.named_weights():
+                if k in o._non_trainable:
+                    dist.broadcast(o._weights[k], src=0)

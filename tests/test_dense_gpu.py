@@ -10,10 +10,11 @@ from util import synth_targets
 pytestmark = pytest.mark.gpu
 
 
-def nerr(got, ref):
+def nerr(got, ref, floor=1e-30):
+    """normalised max error |got-ref|_inf / max(|ref|_inf, floor)."""
     got = np.asarray(got, np.float64)
     ref = np.asarray(ref, np.float64)
-    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), floor))
 
 
 def _perturb(model, rng):
@@ -104,7 +105,9 @@ def test_attention_block_vs_oracle(Lq, Lk, selfattn, dropout):
     if not selfattn:
         errs["d_key"] = nerr(d_k.cpu().numpy(), tk.grad.numpy())
     for n, o, kk in blk.named_weights():
-        errs[n] = nerr(o._grads[kk].cpu().numpy(), p["p/" + n[len("blk/"):]].grad.numpy())
+        # the key-bias gradient is mathematically zero (softmax is shift invariant): use the query-bias scale
+        floor = float(p["p/AttentionLayer/QueryProjection/bias"].grad.abs().max()) if "KeyProjection/bias" in n else 1e-30
+        errs[n] = nerr(o._grads[kk].cpu().numpy(), p["p/" + n[len("blk/"):]].grad.numpy(), floor)
     for n, e in errs.items():
         print(f"  {n}: {e:.2e}")
     assert max(errs.values()) < 2e-5       # fp32 accumulation over up to 800 rows vs fp64
@@ -241,15 +244,23 @@ def test_model_train_step_vs_oracle(N, B, rows, cols, dropout, dataset):
         assert nerr(m[k].cpu().numpy(), out["metrics"][k].detach().numpy()) < 1e-5, k
     assert nerr(m["IOU"].cpu().numpy(), out["metrics"]["IOU"].detach().numpy()) < 1e-4
     g = model.get_grads_dict()
+    assert set(g) == set(grads)
+    # Tolerance: the loss gradient is ill-conditioned in fp32 wherever a cumulative probability sits next
+    # to the .999 clip (d/dp ~ 1/(1-p)), so the yardstick is the oracle itself evaluated in fp32 with the
+    # same assignment: GPU error <= max(2e-5, 5 x fp32-oracle error), both measured against fp64.
+    _, grads32, _ = R.train_step_reference(w, inputs["features"], tg, N, 8, torch.float32,
+                                           dropout_seed=777 if dropout else None, weights=R.model_weights(1.0),
+                                           forced_masks=[m_.to(torch.float32) for m_ in out["masks"]])
+    gmax = max(float(np.abs(v).max()) for v in grads.values())
     worst = []
     for k, ref in grads.items():
-        worst.append((nerr(g[k], ref), k, float(np.abs(ref).max())))
+        floor = 1e-6 * gmax            # tensors whose true gradient is zero (key biases) compare on this scale
+        worst.append((nerr(g[k], ref, floor), nerr(grads32[k], ref, floor), k, float(np.abs(ref).max())))
     worst.sort(reverse=True)
-    for e, k, mag in worst[:8]:
-        print(f"  grad {k}: {e:.2e} (max |ref| {mag:.2e})")
-    assert set(g) == set(grads)
-    # 1e-4: fp32 kernels (sums over up to 800 rows, atomics) against an fp64 reference
-    assert worst[0][0] < 1e-4
+    for e, e32, k, mag in worst[:8]:
+        print(f"  grad {k}: gpu {e:.2e} | fp32 oracle {e32:.2e} (max |ref| {mag:.2e})")
+    for e, e32, k, mag in worst:
+        assert e < max(2e-5, 5 * e32), k
     wd = model.get_weights_dict()
     for k, ref in stats.items():
         assert nerr(wd[k], ref) < 1e-5, k
