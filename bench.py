@@ -141,7 +141,7 @@ def roofline_block(cfg, B, flush, peaks):
     return {"bound": "tensor", "kernel": "attention_fwd (encoder self-attention core, L=%d)" % L,
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if "bf16_tflops" in peaks else "fallback 1590",
-            "gemm_MxNxK": [B * L, D, D], "gemm_tflops": flops_gemm / t_gemm / 1e12, "mode": "bf16" if mode else "fp32"}
+            "gemm_MxNxK": [B * L, D, D], "gemm_tflops": flops_gemm / t_gemm / 1e12, "mode": "tf32" if mode else "fp32"}
 
 
 def cpu_reference_steps(cfg, B, C, A, steps, warmup, threads):
@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("BDETR_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--mode", default=os.environ.get("BDETR_MODE", "fp32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -234,7 +234,7 @@ def main():
     rank, world, local = init_from_env()
     torch.cuda.set_device(local)
     lib = _lib.load()
-    lib.bdetr_set_mode(_lib.MODE_BF16 if args.mode == "bf16" else _lib.MODE_FP32)
+    lib.bdetr_set_mode(_lib.MODE_TF32 if args.mode == "tf32" else _lib.MODE_FP32)
     model = make_model(cfg)
     DataParallel(model)
     batch = synth_batch(rank, B, C, A, cfg)
@@ -313,7 +313,7 @@ def main():
     flops = algorithmic_flops_per_step(cfg, B, C, A)
     line = {"metric": METRIC, "value": B * world / sec_per_step, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "fp32", "data": "synthetic (random-init weights)",
+            "vs_baseline": None, "dtype": "tf32" if args.mode == "tf32" else "fp32", "data": "synthetic (random-init weights)",
             "config": config, "clocks": sampler.summary(),
             "e2e": {"value": B * world / e2e_sec, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_sec * 1e3},

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libbdetr.so")
 
 BDETR_OK = 0
 BDETR_E_BAD_SHAPE, BDETR_E_CUDA, BDETR_E_INVALID_COST, BDETR_E_INFEASIBLE, BDETR_E_NULL, BDETR_E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
-MODE_FP32, MODE_BF16 = 0, 1
+MODE_FP32, MODE_TF32 = 0, 1
 
 
 class BdetrError(RuntimeError):

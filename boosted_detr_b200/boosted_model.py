@@ -267,6 +267,7 @@ class BoostedDETR:
         feats, y_true = self._prepare(inputs, True)
         self.zero_grads()
         y_pred, ctx = self.forward(feats, y_true, True)
+        self.last_ctx_train, self.last_preds = ctx, y_pred
         m = self._collect_metrics(ctx)
         self.backward(ctx, gscale=1.0 / self.num_replicas)
         if self.grad_allreduce is not None:

@@ -24,7 +24,7 @@ extern "C" __attribute__((visibility("default"))) int bdetr_version(void) { retu
 extern "C" __attribute__((visibility("default"))) const char *bdetr_last_error(void) { return bdetr::g_err; }
 extern "C" __attribute__((visibility("default"))) int bdetr_set_mode(int mode)
 {
-    if (mode != BDETR_MODE_FP32 && mode != BDETR_MODE_BF16) {
+    if (mode != BDETR_MODE_FP32 && mode != BDETR_MODE_TF32) {
         bdetr::set_error("bdetr_set_mode: unknown mode %d", mode);
         return BDETR_E_UNSUPPORTED;
     }

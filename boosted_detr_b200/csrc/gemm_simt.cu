@@ -123,6 +123,10 @@ int launch_gemm(int M, int N, int K, const float *A, int lda, bool TA, const flo
 {
     BDETR_REQUIRE(M > 0 && N > 0 && K > 0, BDETR_E_BAD_SHAPE, "M,N,K must be positive");
     BDETR_REQUIRE(A && B && C, BDETR_E_NULL, "null operand");
+    if (current_mode() == BDETR_MODE_TF32 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+        (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
+        umma_gemm_eligible(M, N, K, A, lda, TA, B, ldb, TB, ldc))
+        return launch_gemm_umma(M, N, K, A, lda, TA, B, ldb, TB, bias, act, relu_mask, beta, C, ldc, s);
     GemmArgs g;
     g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.bias = bias; g.act = act;
     g.relu_mask = relu_mask; g.beta = beta; g.C = C; g.ldc = ldc;

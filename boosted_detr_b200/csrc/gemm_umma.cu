@@ -1,0 +1,329 @@
+// Tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
+// tcgen05.mma kind::tf32 with the fp32 accumulator in TMEM -> tcgen05.ld epilogue.
+//
+// Operands are the fp32 activations / weights exactly as they sit in HBM (no conversion pass):
+// TF32 keeps a 10-bit mantissa (>= the reference's mixed_float16 compute type), accumulation is fp32.
+// Both operand majors are supported through the UMMA descriptors, so the three GEMMs of a Dense
+// layer need no transposes:
+//     forward   Y[M,N]  = X[M,K]   W[K,N]      A K-major,  B MN-major
+//     dgrad     dX[M,K] = dY[M,N]  W[K,N]^T    A K-major,  B K-major
+//     wgrad     dW[K,N] += X[M,K]^T dY[M,N]    A MN-major, B MN-major   (split-K, fp32 red.add)
+// One CTA computes one 128 x BN output tile (x one K split): warp 0 = TMA producer, warp 1 = TMEM
+// allocator + single-thread MMA issuer, warps 2-5 = epilogue (one TMEM lane = one output row each).
+#include <cuda.h>
+#include "kernels.cuh"
+
+namespace bdetr {
+
+constexpr int UM_BM = 128;
+constexpr int UM_BK = 32;              // fp32 elements per stage along the contraction = one 128B swizzle row
+constexpr int UM_STAGES = 4;
+constexpr int UM_THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 28;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && ++spins > SPIN_LIMIT) __trap();     // never hang the GPU: a protocol bug becomes an error
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b format TF32=2 [7,10)/[10,13),
+// a_major [15], b_major [16] (1 = MN-major), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, int b_mn)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct UmmaEpilogue {
+    int M, N;
+    const float *bias; int act; const float *relu_mask; int beta; int atomic_out;
+    float *C; int ldc;
+    int num_kb, kb_per_split;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, UmmaEpilogue ep)
+{
+    constexpr uint32_t A_STAGE = UM_BM * UM_BK * 4;      // 16 KB
+    constexpr uint32_t B_STAGE = BN * UM_BK * 4;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // SWIZZLE_128B atoms need 1024B alignment
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + UM_STAGES * A_STAGE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_b + UM_STAGES * B_STAGE);
+    uint64_t *empty = full + UM_STAGES;
+    uint64_t *accum_full = empty + UM_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
+    const int kb_beg = blockIdx.z * ep.kb_per_split;
+    const int kb_end = min(ep.num_kb, kb_beg + ep.kb_per_split);
+    const int nkb = kb_end - kb_beg;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % UM_STAGES;
+                if (i >= UM_STAGES) mbar_wait(&empty[s], ((i / UM_STAGES) - 1) & 1);
+                mbar_expect_tx(&full[s], A_STAGE + B_STAGE);
+                const int k0 = (kb_beg + i) * UM_BK;
+                uint8_t *a_dst = smem_a + s * A_STAGE, *b_dst = smem_b + s * B_STAGE;
+                if (!A_MN) {
+                    tma_load_2d(a_dst, &map_a, k0, m0, &full[s]);                      // box {32 k, 128 rows}
+                } else {
+#pragma unroll
+                    for (int j = 0; j < UM_BM / 32; ++j) tma_load_2d(a_dst + j * 4096, &map_a, m0 + 32 * j, k0, &full[s]);   // box {32 m, 32 k}
+                }
+                if (!B_MN) {
+                    tma_load_2d(b_dst, &map_b, k0, n0, &full[s]);                      // box {32 k, BN rows}
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_dst + j * 4096, &map_b, n0 + 32 * j, k0, &full[s]);      // box {32 n, 32 k}
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(UM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % UM_STAGES;
+                mbar_wait(&full[s], (i / UM_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_base = smem_u32(smem_a + s * A_STAGE), b_base = smem_u32(smem_b + s * B_STAGE);
+#pragma unroll
+                for (int j = 0; j < UM_BK / 8; ++j) {                                   // UMMA_K = 8 for tf32
+                    // K-major: 8 rows x 128B atoms, 1024B apart; advance 32B per k-step inside the swizzled row.
+                    // MN-major: [mn-block of 32][k row][128B]; blocks 4096B apart; 8 k-rows = 1024B per k-step.
+                    const uint64_t a_desc = A_MN ? make_smem_desc(a_base + j * 1024, 4096, 1024) : make_smem_desc(a_base + j * 32, 16, 1024);
+                    const uint64_t b_desc = B_MN ? make_smem_desc(b_base + j * 1024, 4096, 1024) : make_smem_desc(b_base + j * 32, 16, 1024);
+                    umma_tf32(tmem_base, a_desc, b_desc, idesc, (i | j) != 0);
+                }
+                umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
+            }
+            umma_commit(accum_full);               // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warp w owns TMEM lanes 32*(w%4).. =====
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        if (nkb > 0) {
+            mbar_wait(accum_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+            }
+            if (row < ep.M) {
+                float *crow = ep.C + (size_t)row * ep.ldc;
+                const float *mrow = ep.relu_mask ? ep.relu_mask + (size_t)row * ep.ldc : nullptr;
+                if (!ep.atomic_out && n0 + c0 + 32 <= ep.N) {
+                    // full 32-column chunk: 16-byte accesses (ldc % 4 == 0 and C is 16B aligned by eligibility)
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const int n = n0 + c0 + i;
+                        float4 x = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (ep.bias) { const float4 b = *reinterpret_cast<const float4 *>(ep.bias + n); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+                        if (ep.beta) { const float4 c = *reinterpret_cast<const float4 *>(crow + n); x.x += c.x; x.y += c.y; x.z += c.z; x.w += c.w; }
+                        if (ep.act == 1) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                        if (mrow) {
+                            const float4 k = *reinterpret_cast<const float4 *>(mrow + n);
+                            if (!(k.x > 0.f)) x.x = 0.f; if (!(k.y > 0.f)) x.y = 0.f; if (!(k.z > 0.f)) x.z = 0.f; if (!(k.w > 0.f)) x.w = 0.f;
+                        }
+                        *reinterpret_cast<float4 *>(crow + n) = x;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int n = n0 + c0 + i;
+                        if (n < ep.N) {
+                            float x = v[i];
+                            if (ep.atomic_out) {
+                                if (ep.bias && blockIdx.z == 0) x += ep.bias[n];
+                                atomicAdd(crow + n, x);
+                            } else {
+                                if (ep.bias) x += ep.bias[n];
+                                if (ep.beta) x += crow[n];
+                                if (ep.act == 1) x = fmaxf(x, 0.0f);
+                                if (mrow && !(mrow[n] > 0.0f)) x = 0.0f;
+                                crow[n] = x;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool encode_map(CUtensorMap *map, const float *base, int rows, int cols, int ld, int box_cols, int box_rows)
+{
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int BN>
+static size_t umma_smem_bytes() { return (size_t)UM_STAGES * (UM_BM * UM_BK * 4 + BN * UM_BK * 4) + (2 * UM_STAGES + 1) * 8 + 16 + 1024; }
+
+bool umma_gemm_eligible(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB, int ldc)
+{
+    (void)TA; (void)TB;
+    auto ok = [](const void *p, int ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 4 == 0; };
+    return ok(A, lda) && ok(B, ldb) && ldc % 4 == 0 && K >= 32 && N >= 64 && M >= 128;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_umma_inst(dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const UmmaEpilogue &ep, cudaStream_t s)
+{
+    static bool optin = false;
+    const size_t smem = umma_smem_bytes<BN>();
+    if (!optin) {
+        BDETR_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        optin = true;
+    }
+    gemm_umma_kernel<BN, A_MN, B_MN><<<grid, UM_THREADS, smem, s>>>(ma, mb, ep);
+    BDETR_CHECK_LAUNCH("gemm_umma_kernel");
+    return BDETR_OK;
+}
+
+// Same contract as launch_gemm (gemm_simt.cu).  TA: A stored [K,M]; TB: B stored [N,K].
+int launch_gemm_umma(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB,
+                     const float *bias, int act, const float *relu_mask, int beta, float *C, int ldc, cudaStream_t s)
+{
+    // operand majors: A K-major when stored [M,K]; MN-major when stored [K,M].  B K-major when stored [N,K];
+    // MN-major when stored [K,N] (Keras kernels and dY).
+    const bool A_MN = TA, B_MN = !TB;
+    const int BN = (N >= 128) ? 128 : 64;
+    CUtensorMap ma, mb;
+    bool ok;
+    if (!A_MN) ok = encode_map(&ma, A, M, K, lda, UM_BK, UM_BM);          // [M rows, K cols], box {32 k, 128 m}
+    else ok = encode_map(&ma, A, K, M, lda, 32, UM_BK);                   // [K rows, M cols], box {32 m, 32 k}
+    if (!B_MN) ok = ok && encode_map(&mb, B, N, K, ldb, UM_BK, BN);       // [N rows, K cols], box {32 k, BN n}
+    else ok = ok && encode_map(&mb, B, K, N, ldb, 32, UM_BK);             // [K rows, N cols], box {32 n, 32 k}
+    BDETR_REQUIRE(ok, BDETR_E_CUDA, "cuTensorMapEncodeTiled failed");
+
+    UmmaEpilogue ep;
+    ep.M = M; ep.N = N; ep.bias = bias; ep.act = act; ep.relu_mask = relu_mask; ep.beta = beta; ep.C = C; ep.ldc = ldc;
+    ep.num_kb = ceil_div(K, UM_BK);
+    const int tiles = ceil_div(M, UM_BM) * ceil_div(N, BN);
+    int splits = 1;
+    if (act == 0 && relu_mask == nullptr && tiles < 74 && ep.num_kb >= 16) splits = min(ep.num_kb / 4, max(1, 148 / tiles));
+    ep.kb_per_split = ceil_div(ep.num_kb, splits);
+    splits = ceil_div(ep.num_kb, ep.kb_per_split);
+    ep.atomic_out = splits > 1;
+    if (ep.atomic_out && !beta) BDETR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, s));
+    dim3 grid(ceil_div(N, BN), ceil_div(M, UM_BM), splits);
+#define UMMA_DISPATCH(BN_)                                                                            \
+    do {                                                                                              \
+        if (!A_MN && B_MN) return launch_umma_inst<BN_, false, true>(grid, ma, mb, ep, s);            \
+        if (!A_MN && !B_MN) return launch_umma_inst<BN_, false, false>(grid, ma, mb, ep, s);          \
+        if (A_MN && B_MN) return launch_umma_inst<BN_, true, true>(grid, ma, mb, ep, s);              \
+        return launch_umma_inst<BN_, true, false>(grid, ma, mb, ep, s);                               \
+    } while (0)
+    if (BN == 128) UMMA_DISPATCH(128);
+    UMMA_DISPATCH(64);
+#undef UMMA_DISPATCH
+}
+
+}  // namespace bdetr

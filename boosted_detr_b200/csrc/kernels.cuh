@@ -12,6 +12,11 @@ int current_mode();
 int launch_gemm(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB,
                 const float *bias, int act, const float *relu_mask, int beta, float *C, int ldc, cudaStream_t s);
 
+// tcgen05 / TMA / TMEM tensor-core path (gemm_umma.cu), same contract as launch_gemm
+bool umma_gemm_eligible(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB, int ldc);
+int launch_gemm_umma(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB,
+                     const float *bias, int act, const float *relu_mask, int beta, float *C, int ldc, cudaStream_t s);
+
 // dst[n] += sum_m src[m, n]
 int launch_colsum_acc(int M, int N, const float *src, float *dst, cudaStream_t s);
 

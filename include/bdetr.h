@@ -36,7 +36,7 @@ typedef enum {
 
 /* compute modes for the dense (GEMM / attention) kernels */
 #define BDETR_MODE_FP32 0 /* fp32 SIMT FFMA everywhere: the 1e-5 parity mode                   */
-#define BDETR_MODE_BF16 1 /* bf16 operands, fp32 accumulate on tcgen05 tensor cores (1e-3 mode) */
+#define BDETR_MODE_TF32 1 /* TF32 operands (10-bit mantissa) via TMA, fp32 accumulate in TMEM on tcgen05 (1e-3 mode) */
 
 int bdetr_version(void);
 const char *bdetr_last_error(void);

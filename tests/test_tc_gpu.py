@@ -1,0 +1,89 @@
+"""Tensor-core mode (TF32 operands through TMA + tcgen05.mma, fp32 accumulation in TMEM) against the fp64
+oracle.  Tolerance: 1e-3 relative on losses / predictions (north_star's reduced-precision bar)."""
+import numpy as np
+import pytest
+import torch
+
+from test_dense_gpu import _model_and_data, nerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def tc_mode():
+    from boosted_detr_b200 import _lib
+    lib = _lib.load()
+    lib.bdetr_set_mode(_lib.MODE_TF32)
+    yield
+    lib.bdetr_set_mode(_lib.MODE_FP32)
+
+
+def test_umma_gemm_variants(tc_mode):
+    from boosted_detr_b200 import _lib
+    from boosted_detr_b200.device import ptr, stream_ptr
+    rng = np.random.default_rng(0)
+    cases = [  # M, N, K, ta, tb, bias, act, beta
+        (6400, 256, 256, 0, 0, 1, 1, 0),      # forward Dense (A K-major, B MN-major)
+        (1600, 256, 256, 0, 0, 1, 0, 0),      # ragged M (12.5 tiles)
+        (6400, 256, 256, 0, 1, 0, 0, 1),      # dgrad (both K-major), accumulate
+        (256, 256, 6400, 1, 0, 0, 0, 1),      # wgrad (both MN-major), split-K atomics, accumulate
+        (256, 256, 1600, 1, 0, 0, 0, 0),      # wgrad overwrite (memset + atomics)
+        (1000, 192, 96, 0, 0, 1, 0, 0),       # odd sizes: N tail, K = 3 k-blocks
+        (300, 64, 40, 0, 1, 0, 0, 0),         # K tail handled by TMA zero fill
+        (128, 128, 32, 1, 1, 0, 0, 0),        # A MN-major, B K-major
+    ]
+    for (M, N, K, ta, tb, bias, act, beta) in cases:
+        A = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+        Bm = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+        bv = rng.standard_normal(N).astype(np.float32)
+        C0 = rng.standard_normal((M, N)).astype(np.float32)
+        ref = (A.T if ta else A).astype(np.float64) @ (Bm.T if tb else Bm).astype(np.float64)
+        if bias:
+            ref = ref + bv
+        if beta:
+            ref = ref + C0
+        if act:
+            ref = np.maximum(ref, 0)
+        dA, dB, db, dC = (torch.from_numpy(x).cuda() for x in (A, Bm, bv, C0.copy()))
+        _lib.call("bdetr_gemm", M, N, K, ptr(dA), ta, ptr(dB), tb, ptr(db) if bias else None, act, beta, ptr(dC), stream_ptr())
+        torch.cuda.synchronize()
+        e = nerr(dC.cpu().numpy(), ref)
+        print(f"umma gemm M{M} N{N} K{K} ta{ta} tb{tb} bias{bias} act{act} beta{beta}: {e:.2e}")
+        assert 1e-7 < e < 2e-3, "error must look like TF32 rounding (not fp32-exact, not garbage)"
+
+
+def test_model_train_step_tf32(tc_mode):
+    from oracle import reference_path as R
+    N, B = 2, 2
+    model, w, inputs = _model_and_data(N=N, B=B, rows=20, cols=20)
+    logs = model.train_step(inputs)
+    tg = (inputs["category"], inputs["attribute"], inputs["bbox"], inputs["num_objects"])
+    # the assignment is discrete: force the oracle onto the GPU's assignment so that tolerances are meaningful,
+    # and separately require that the assignments agree with the oracle's own on this data
+    masks = []
+    for c in model.last_ctx_train["loss"]:
+        c4r = c["col4row"].cpu().numpy()
+        m = np.zeros(c["dims"][:3], np.float32)
+        bb, tt = np.nonzero(c4r >= 0)
+        m[bb, tt, c4r[bb, tt]] = 1.0
+        masks.append(torch.tensor(m, dtype=torch.float64))
+    out, grads, stats = R.train_step_reference(w, inputs["features"], tg, N, 8, torch.float64, weights=R.model_weights(1.0),
+                                               forced_masks=masks)
+    own, _, _ = R.train_step_reference(w, inputs["features"], tg, N, 8, torch.float64, weights=R.model_weights(1.0))
+    flips = sum(int((a.numpy() != b.numpy()).sum()) // 2 for a, b in zip(own["masks"], masks))
+    print("assignment flips vs fp64 oracle:", flips)
+    m = model.metric_tensors
+    e = nerr(m["loss"].cpu().numpy(), out["loss"].detach().numpy())
+    print(f"tf32 loss vector: {e:.2e}")
+    assert e < 1e-3
+    for g_, r_, name in zip(model.last_preds, out["preds"], ["cat", "attr", "box"]):
+        e = nerr(g_.cpu().numpy(), r_.detach().numpy())
+        print(f"tf32 {name} preds: {e:.2e}")
+        assert e < 1e-3
+    g = model.get_grads_dict()
+    gmax = max(float(np.abs(v).max()) for v in grads.values())
+    worst = sorted(((nerr(g[k], ref, 1e-6 * gmax), k) for k, ref in grads.items()), reverse=True)
+    for e, k in worst[:6]:
+        print(f"  tf32 grad {k}: {e:.2e}")
+    assert worst[0][0] < 5e-2          # gradients through two boosted blocks with TF32 products
+    assert flips == 0
