@@ -81,14 +81,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32])
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout the hardware
+// accepts for MN-major 32-bit operands: 128B rows, 4-row atoms, 32B chunks XOR-swizzled by row % 4).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type)
 {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b format TF32=2 [7,10)/[10,13),
@@ -175,10 +177,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const uint32_t a_base = smem_u32(smem_a + s * A_STAGE), b_base = smem_u32(smem_b + s * B_STAGE);
 #pragma unroll
                 for (int j = 0; j < UM_BK / 8; ++j) {                                   // UMMA_K = 8 for tf32
-                    // K-major: 8 rows x 128B atoms, 1024B apart; advance 32B per k-step inside the swizzled row.
-                    // MN-major: [mn-block of 32][k row][128B]; blocks 4096B apart; 8 k-rows = 1024B per k-step.
-                    const uint64_t a_desc = A_MN ? make_smem_desc(a_base + j * 1024, 4096, 1024) : make_smem_desc(a_base + j * 32, 16, 1024);
-                    const uint64_t b_desc = B_MN ? make_smem_desc(b_base + j * 1024, 4096, 1024) : make_smem_desc(b_base + j * 32, 16, 1024);
+                    // K-major: 8 rows x 128B atoms, 1024B apart (SBO); advance 32B per k-step inside the swizzled row.
+                    // MN-major: [mn-block of 32][k row][128B]; mn-blocks 4096B apart (LBO); 4-k-row atoms 512B apart
+                    // (SBO); one k-step = 8 k-rows = 1024B.
+                    const uint64_t a_desc = A_MN ? make_smem_desc(a_base + j * 1024, 4096, 512, 1) : make_smem_desc(a_base + j * 32, 16, 1024, 2);
+                    const uint64_t b_desc = B_MN ? make_smem_desc(b_base + j * 1024, 4096, 512, 1) : make_smem_desc(b_base + j * 32, 16, 1024, 2);
                     umma_tf32(tmem_base, a_desc, b_desc, idesc, (i | j) != 0);
                 }
                 umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
@@ -251,14 +254,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static bool encode_map(CUtensorMap *map, const float *base, int rows, int cols, int ld, int box_cols, int box_rows)
+static bool encode_map(CUtensorMap *map, const float *base, int rows, int cols, int ld, int box_cols, int box_rows, bool mn_major)
 {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -297,10 +300,10 @@ int launch_gemm_umma(int M, int N, int K, const float *A, int lda, bool TA, cons
     const int BN = (N >= 128) ? 128 : 64;
     CUtensorMap ma, mb;
     bool ok;
-    if (!A_MN) ok = encode_map(&ma, A, M, K, lda, UM_BK, UM_BM);          // [M rows, K cols], box {32 k, 128 m}
-    else ok = encode_map(&ma, A, K, M, lda, 32, UM_BK);                   // [K rows, M cols], box {32 m, 32 k}
-    if (!B_MN) ok = ok && encode_map(&mb, B, N, K, ldb, UM_BK, BN);       // [N rows, K cols], box {32 k, BN n}
-    else ok = ok && encode_map(&mb, B, K, N, ldb, 32, UM_BK);             // [K rows, N cols], box {32 n, 32 k}
+    if (!A_MN) ok = encode_map(&ma, A, M, K, lda, UM_BK, UM_BM, false);          // [M rows, K cols], box {32 k, 128 m}
+    else ok = encode_map(&ma, A, K, M, lda, 32, UM_BK, true);                   // [K rows, M cols], box {32 m, 32 k}
+    if (!B_MN) ok = ok && encode_map(&mb, B, N, K, ldb, UM_BK, BN, false);       // [N rows, K cols], box {32 k, BN n}
+    else ok = ok && encode_map(&mb, B, K, N, ldb, 32, UM_BK, true);             // [K rows, N cols], box {32 n, 32 k}
     BDETR_REQUIRE(ok, BDETR_E_CUDA, "cuTensorMapEncodeTiled failed");
 
     UmmaEpilogue ep;
