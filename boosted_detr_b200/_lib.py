@@ -31,7 +31,7 @@ FfnParams = _ptr_struct("FfnParams", ["w1", "b1", "w2", "b2", "ln_gamma", "ln_be
 FfnSaved = _ptr_struct("FfnSaved", ["h", "z", "mean", "rstd"])
 FfnScratch = _ptr_struct("FfnScratch", ["d_z", "d_h"])
 HeadParams = _ptr_struct("HeadParams", ["w1", "b1", "bn_gamma", "bn_beta", "bn_moving_mean", "bn_moving_var", "w2", "b2"])
-HeadSaved = _ptr_struct("HeadSaved", ["h", "hn", "bn_mean", "bn_rstd", "act"])
+HeadSaved = _ptr_struct("HeadSaved", ["h", "hn", "bn_mean", "bn_rstd", "bn_acc", "act"])
 HeadScratch = _ptr_struct("HeadScratch", ["d_logits", "d_hn", "d_h"])
 
 P = c_void_p
@@ -63,6 +63,7 @@ PROTOTYPES = {
     "bdetr_add_positional_bwd": (c_int, [I, I, I, P, P, P]),
     "bdetr_tile_queries_fwd": (c_int, [I, I, I, P, P, P]),
     "bdetr_accumulate": (c_int, [c_size_t, P, P, P]),
+    "bdetr_round_tf32": (c_int, [c_size_t, P, P, P]),
     "bdetr_head_fwd": (c_int, [I, I, I, I, I, I, F, P, POINTER(HeadParams), F, F, P, I, POINTER(HeadSaved), P]),
     "bdetr_head_bwd": (c_int, [I, I, I, I, I, F, P, POINTER(HeadParams), F, POINTER(HeadSaved), P, P, I,
                                POINTER(HeadParams), POINTER(HeadScratch), P]),

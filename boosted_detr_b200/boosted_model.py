@@ -105,15 +105,26 @@ class BoostedDETR:
             w = o._weights[k]
             self._index[n] = (off, w.numel(), tuple(w.shape))
             off += (w.numel() + 3) // 4 * 4               # keep every tensor 16-byte aligned
-        flat_w, flat_g = zeros(off), zeros(off)
+        flat_w, flat_g, flat_tc = zeros(off), zeros(off), zeros(off)
         for n, o, k in named:
             o0, cnt, shp = self._index[n]
             flat_w[o0:o0 + cnt].copy_(o._weights[k].reshape(-1))
             o._weights[k] = flat_w[o0:o0 + cnt].view(shp)
             o._grads[k] = flat_g[o0:o0 + cnt].view(shp)
+            if k.endswith("/kernel"):
+                o._shadow[k] = flat_tc[o0:o0 + cnt].view(shp)     # tf32-rounded copy read by the tcgen05 GEMMs
         self._flat = (flat_w, flat_g)
+        self._flat_tc = flat_tc
         for layer in self.layers():
             layer.invalidate()
+
+    def tensor_core_mode(self):
+        return _lib.load().bdetr_get_mode() == _lib.MODE_TF32
+
+    def refresh_shadow(self):
+        """tensor-core mode: re-round the Dense kernels into their tf32 shadows (one pass over the flat buffer)."""
+        if self._flat is not None and self.tensor_core_mode():
+            _lib.call("bdetr_round_tf32", self._flat[0].numel(), ptr(self._flat[0]), ptr(self._flat_tc), stream_ptr())
 
     def num_parameters(self, include_non_trainable=True):
         return sum(o._weights[k].numel() for _, o, k in self.named_weights()
@@ -182,6 +193,10 @@ class BoostedDETR:
         N = self.num_decoder_blocks
         use_dropout = training and self.dropout_seed is not None
         x = feats
+        if self.tensor_core_mode():
+            self.refresh_shadow()
+            x = torch.empty_like(feats)                        # the block input feeds tcgen05 GEMMs: round it too
+            _lib.call("bdetr_round_tf32", feats.numel(), ptr(feats), ptr(x), stream_ptr())
         cums = None
         blocks, loss_ctxs = [], []
         for i in range(N):

@@ -62,7 +62,7 @@ __device__ __forceinline__ void stage_rows(float (*dst)[HD], const float *src, s
 
 __global__ void __launch_bounds__(AT_THREADS)
 attention_fwd_kernel(int H, int Lq, int Lk, const float *__restrict__ qp, const float *__restrict__ kp,
-                     const float *__restrict__ vp, float *__restrict__ o, float *__restrict__ lse, float scale_log2)
+                     const float *__restrict__ vp, float *__restrict__ o, float *__restrict__ lse, float scale_log2, int round_out)
 {
     __shared__ __align__(16) float Ks[AT_TILE][HD];
     __shared__ __align__(16) float Vs[AT_TILE][HD];
@@ -110,7 +110,7 @@ attention_fwd_kernel(int H, int Lq, int Lk, const float *__restrict__ qp, const 
     if (live) {
         const float inv = 1.0f / l;
 #pragma unroll
-        for (int k = 0; k < HD; ++k) acc[k] *= inv;
+        for (int k = 0; k < HD; ++k) acc[k] = maybe_tf32(acc[k] * inv, round_out);
         store_row32(o + (((size_t)b * H + h) * Lq + i) * HD, acc);
         lse[((size_t)b * H + h) * Lq + i] = m + log2f(l);     // log2 units
     }
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(AT_THREADS)
 attention_bwd_dq_kernel(int H, int Lq, int Lk, const float *__restrict__ qp, const float *__restrict__ kp,
                         const float *__restrict__ vp, const float *__restrict__ o, const float *__restrict__ lse,
                         const float *__restrict__ d_o, float *__restrict__ delta, float *__restrict__ d_qp,
-                        float scale, float scale_log2)
+                        float scale, float scale_log2, int round_out)
 {
     __shared__ __align__(16) float Ks[AT_TILE][HD];
     __shared__ __align__(16) float Vs[AT_TILE][HD];
@@ -160,7 +160,11 @@ attention_bwd_dq_kernel(int H, int Lq, int Lk, const float *__restrict__ qp, con
             axpy32(dq, ds, Ks[j]);
         }
     }
-    if (live) store_row32(d_qp + ((size_t)b * Lq + i) * D + h * HD, dq);
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < HD; ++k) dq[k] = maybe_tf32(dq[k], round_out);
+        store_row32(d_qp + ((size_t)b * Lq + i) * D + h * HD, dq);
+    }
 }
 
 // dK, dV: thread = key row; queries / dO / lse / delta staged in shared memory.
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(AT_THREADS)
 attention_bwd_dkv_kernel(int H, int Lq, int Lk, const float *__restrict__ qp, const float *__restrict__ kp,
                          const float *__restrict__ vp, const float *__restrict__ lse, const float *__restrict__ d_o,
                          const float *__restrict__ delta, float *__restrict__ d_kp, float *__restrict__ d_vp,
-                         float scale, float scale_log2)
+                         float scale, float scale_log2, int round_out)
 {
     __shared__ __align__(16) float Qs[AT_TILE][HD];
     __shared__ __align__(16) float Gs[AT_TILE][HD];
@@ -206,34 +210,36 @@ attention_bwd_dkv_kernel(int H, int Lq, int Lk, const float *__restrict__ qp, co
         }
     }
     if (live) {
+#pragma unroll
+        for (int k = 0; k < HD; ++k) { dk[k] = maybe_tf32(dk[k], round_out); dv[k] = maybe_tf32(dv[k], round_out); }
         store_row32(d_kp + ((size_t)b * Lk + j) * D + h * HD, dk);
         store_row32(d_vp + ((size_t)b * Lk + j) * D + h * HD, dv);
     }
 }
 
 int launch_attention_fwd(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
-                         float *o, float *lse, cudaStream_t s)
+                         float *o, float *lse, int round_out, cudaStream_t s)
 {
     BDETR_REQUIRE(d == HD, BDETR_E_UNSUPPORTED, "head dim must be 32 (D/H)");
     BDETR_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0, BDETR_E_BAD_SHAPE, "bad attention shape");
     const float scale = 1.0f / sqrtf((float)d);
     dim3 grid(ceil_div(Lq, AT_THREADS), H, B);
-    attention_fwd_kernel<<<grid, AT_THREADS, 0, s>>>(H, Lq, Lk, qp, kp, vp, o, lse, scale * LOG2E);
+    attention_fwd_kernel<<<grid, AT_THREADS, 0, s>>>(H, Lq, Lk, qp, kp, vp, o, lse, scale * LOG2E, round_out);
     BDETR_CHECK_LAUNCH("attention_fwd_kernel");
     return BDETR_OK;
 }
 
 int launch_attention_bwd(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
                          const float *o, const float *lse, const float *d_o, float *delta,
-                         float *d_qp, float *d_kp, float *d_vp, cudaStream_t s)
+                         float *d_qp, float *d_kp, float *d_vp, int round_out, cudaStream_t s)
 {
     BDETR_REQUIRE(d == HD, BDETR_E_UNSUPPORTED, "head dim must be 32 (D/H)");
     const float scale = 1.0f / sqrtf((float)d);
     dim3 gq(ceil_div(Lq, AT_THREADS), H, B);
-    attention_bwd_dq_kernel<<<gq, AT_THREADS, 0, s>>>(H, Lq, Lk, qp, kp, vp, o, lse, d_o, delta, d_qp, scale, scale * LOG2E);
+    attention_bwd_dq_kernel<<<gq, AT_THREADS, 0, s>>>(H, Lq, Lk, qp, kp, vp, o, lse, d_o, delta, d_qp, scale, scale * LOG2E, round_out);
     BDETR_CHECK_LAUNCH("attention_bwd_dq_kernel");
     dim3 gk(ceil_div(Lk, AT_THREADS), H, B);
-    attention_bwd_dkv_kernel<<<gk, AT_THREADS, 0, s>>>(H, Lq, Lk, qp, kp, vp, lse, d_o, delta, d_kp, d_vp, scale, scale * LOG2E);
+    attention_bwd_dkv_kernel<<<gk, AT_THREADS, 0, s>>>(H, Lq, Lk, qp, kp, vp, lse, d_o, delta, d_kp, d_vp, scale, scale * LOG2E, round_out);
     BDETR_CHECK_LAUNCH("attention_bwd_dkv_kernel");
     return BDETR_OK;
 }

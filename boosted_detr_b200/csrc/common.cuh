@@ -60,6 +60,16 @@ __host__ inline uint32_t dropout_threshold(float rate)
     return (uint32_t)t;
 }
 
+// round-to-nearest fp32 -> tf32 (10-bit mantissa).  In tensor-core mode every tensor that feeds a tcgen05
+// GEMM is stored already rounded, so the MMA's operand truncation is exact (no truncation bias).
+__device__ __forceinline__ float tf32_rn(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float maybe_tf32(float x, int on) { return on ? tf32_rn(x) : x; }
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll

@@ -11,7 +11,7 @@ struct GemmArgs {
     int M, N, K;
     const float *A; int lda;
     const float *B; int ldb;
-    const float *bias; int act; const float *relu_mask; int beta;
+    const float *bias; int act; const float *relu_mask; int beta; int round_out;
     float *C; int ldc;
     int k_chunk;          // K range per blockIdx.z
     int vecA, vecB;       // 16-byte vector loads are legal for this operand
@@ -103,6 +103,7 @@ gemm_simt_kernel(GemmArgs g)
                 if (g.beta) v += *c;
                 if (g.act == 1) v = fmaxf(v, 0.0f);
                 if (g.relu_mask && !(g.relu_mask[(size_t)m * g.ldc + n] > 0.0f)) v = 0.0f;
+                if (g.round_out) v = tf32_rn(v);
                 *c = v;
             }
         }
@@ -119,22 +120,23 @@ __global__ void zero_strided_kernel(int M, int N, float *C, int ldc)
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int launch_gemm(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB,
-                const float *bias, int act, const float *relu_mask, int beta, float *C, int ldc, cudaStream_t s)
+                const float *bias, int act, const float *relu_mask, int beta, int round_out, float *C, int ldc,
+                cudaStream_t s)
 {
     BDETR_REQUIRE(M > 0 && N > 0 && K > 0, BDETR_E_BAD_SHAPE, "M,N,K must be positive");
     BDETR_REQUIRE(A && B && C, BDETR_E_NULL, "null operand");
     if (current_mode() == BDETR_MODE_TF32 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
         (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
         umma_gemm_eligible(M, N, K, A, lda, TA, B, ldb, TB, ldc))
-        return launch_gemm_umma(M, N, K, A, lda, TA, B, ldb, TB, bias, act, relu_mask, beta, C, ldc, s);
+        return launch_gemm_umma(M, N, K, A, lda, TA, B, ldb, TB, bias, act, relu_mask, beta, round_out, C, ldc, s);
     GemmArgs g;
     g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.bias = bias; g.act = act;
-    g.relu_mask = relu_mask; g.beta = beta; g.C = C; g.ldc = ldc;
+    g.relu_mask = relu_mask; g.beta = beta; g.round_out = round_out; g.C = C; g.ldc = ldc;
     g.vecA = aligned16(A) && (lda % 4 == 0);
     g.vecB = aligned16(B) && (ldb % 4 == 0);
     const int tiles = ceil_div(M, GBM) * ceil_div(N, GBN);
     int splits = 1;
-    if (act == 0 && relu_mask == nullptr && tiles < 96 && K >= 512) {
+    if (act == 0 && relu_mask == nullptr && !round_out && tiles < 96 && K >= 512) {
         splits = min(ceil_div(K, 256), max(1, 296 / tiles));
     }
     g.k_chunk = ceil_div(ceil_div(K, splits), GBK) * GBK;
@@ -153,7 +155,28 @@ int launch_gemm(int M, int N, int K, const float *A, int lda, bool TA, const flo
     return BDETR_OK;
 }
 
-// dst[n] += sum_m src[m,n]: CTA = 32 columns x 8 row-lanes over a row chunk
+// dst[n] += sum_m src[m,n].  CTA = 128 columns (float4 per thread) x 8 row-lanes over a 64-row chunk; scalar
+// fallback when N is not a multiple of 4.
+__global__ void __launch_bounds__(256)
+colsum_acc_kernel_v4(int M, int N, const float *__restrict__ src, float *__restrict__ dst, int rows_per_cta)
+{
+    __shared__ float4 red[8][32];
+    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int c = blockIdx.x * 128 + lane * 4;
+    const int rbeg = blockIdx.y * rows_per_cta, rend = min(M, rbeg + rows_per_cta);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < N) for (int m = rbeg + r; m < rend; m += 8) {
+        const float4 v = *reinterpret_cast<const float4 *>(src + (size_t)m * N + c);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    red[r][lane] = s;
+    __syncthreads();
+    if (r == 0 && c < N) {
+        float4 t = red[0][lane];
+        for (int k = 1; k < 8; ++k) { const float4 v = red[k][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+        atomicAdd(&dst[c], t.x); atomicAdd(&dst[c + 1], t.y); atomicAdd(&dst[c + 2], t.z); atomicAdd(&dst[c + 3], t.w);
+    }
+}
 __global__ void __launch_bounds__(256)
 colsum_acc_kernel(int M, int N, const float *__restrict__ src, float *__restrict__ dst, int rows_per_cta)
 {
@@ -174,9 +197,15 @@ colsum_acc_kernel(int M, int N, const float *__restrict__ src, float *__restrict
 int launch_colsum_acc(int M, int N, const float *src, float *dst, cudaStream_t s)
 {
     BDETR_REQUIRE(M > 0 && N > 0 && src && dst, BDETR_E_BAD_SHAPE, "bad colsum arguments");
-    const int rows_per_cta = 256;
-    dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_cta));
-    colsum_acc_kernel<<<grid, 256, 0, s>>>(M, N, src, dst, rows_per_cta);
+    if (N % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int rows_per_cta = 64;
+        dim3 grid(ceil_div(N, 128), ceil_div(M, rows_per_cta));
+        colsum_acc_kernel_v4<<<grid, 256, 0, s>>>(M, N, src, dst, rows_per_cta);
+    } else {
+        const int rows_per_cta = 256;
+        dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_cta));
+        colsum_acc_kernel<<<grid, 256, 0, s>>>(M, N, src, dst, rows_per_cta);
+    }
     BDETR_CHECK_LAUNCH("colsum_acc_kernel");
     return BDETR_OK;
 }

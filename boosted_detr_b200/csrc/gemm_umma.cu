@@ -17,7 +17,6 @@ namespace bdetr {
 
 constexpr int UM_BM = 128;
 constexpr int UM_BK = 32;              // fp32 elements per stage along the contraction = one 128B swizzle row
-constexpr int UM_STAGES = 4;
 constexpr int UM_THREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
 
@@ -103,12 +102,12 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, i
 
 struct UmmaEpilogue {
     int M, N;
-    const float *bias; int act; const float *relu_mask; int beta; int atomic_out;
+    const float *bias; int act; const float *relu_mask; int beta; int atomic_out; int round_out;
     float *C; int ldc;
     int num_kb, kb_per_split;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, int UM_STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, UmmaEpilogue ep)
 {
@@ -122,6 +121,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t *empty = full + UM_STAGES;
     uint64_t *accum_full = empty + UM_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+    float (*stage)[32][33] = reinterpret_cast<float (*)[32][33]>(tmem_slot + 4);     // per-epilogue-warp transpose buffer
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
@@ -189,13 +189,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             umma_commit(accum_full);               // accumulator complete
         }
     } else {
-        // ===== epilogue: warp w owns TMEM lanes 32*(w%4).. =====
+        // ===== epilogue: warp w owns TMEM lanes 32*(w%4)..; each 32x32 block is transposed through shared
+        // memory so that global stores / reductions are 128-byte coalesced rows =====
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
         if (nkb > 0) {
             mbar_wait(accum_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
+        const int rows_left = ep.M - (m0 + q * 32);
+        const int nrows = rows_left < 32 ? (rows_left < 0 ? 0 : rows_left) : 32;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             float v[32];
@@ -204,44 +206,27 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.0f;
             }
-            if (row < ep.M) {
-                float *crow = ep.C + (size_t)row * ep.ldc;
-                const float *mrow = ep.relu_mask ? ep.relu_mask + (size_t)row * ep.ldc : nullptr;
-                if (!ep.atomic_out && n0 + c0 + 32 <= ep.N) {
-                    // full 32-column chunk: 16-byte accesses (ldc % 4 == 0 and C is 16B aligned by eligibility)
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const int n = n0 + c0 + i;
-                        float4 x = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        if (ep.bias) { const float4 b = *reinterpret_cast<const float4 *>(ep.bias + n); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
-                        if (ep.beta) { const float4 c = *reinterpret_cast<const float4 *>(crow + n); x.x += c.x; x.y += c.y; x.z += c.z; x.w += c.w; }
-                        if (ep.act == 1) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                        if (mrow) {
-                            const float4 k = *reinterpret_cast<const float4 *>(mrow + n);
-                            if (!(k.x > 0.f)) x.x = 0.f; if (!(k.y > 0.f)) x.y = 0.f; if (!(k.z > 0.f)) x.z = 0.f; if (!(k.w > 0.f)) x.w = 0.f;
-                        }
-                        *reinterpret_cast<float4 *>(crow + n) = x;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int n = n0 + c0 + i;
-                        if (n < ep.N) {
-                            float x = v[i];
-                            if (ep.atomic_out) {
-                                if (ep.bias && blockIdx.z == 0) x += ep.bias[n];
-                                atomicAdd(crow + n, x);
-                            } else {
-                                if (ep.bias) x += ep.bias[n];
-                                if (ep.beta) x += crow[n];
-                                if (ep.act == 1) x = fmaxf(x, 0.0f);
-                                if (mrow && !(mrow[n] > 0.0f)) x = 0.0f;
-                                crow[n] = x;
-                            }
-                        }
+            for (int i = 0; i < 32; ++i) stage[q][lane][i] = v[i];
+            __syncwarp();
+            const int n = n0 + c0 + lane;
+            if (n < ep.N) {
+                const float bias_n = (ep.bias && (!ep.atomic_out || blockIdx.z == 0)) ? ep.bias[n] : 0.0f;
+                for (int r = 0; r < nrows; ++r) {
+                    const size_t off = (size_t)(m0 + q * 32 + r) * ep.ldc + n;
+                    float x = stage[q][r][lane] + bias_n;
+                    if (ep.atomic_out) {
+                        atomicAdd(ep.C + off, x);
+                    } else {
+                        if (ep.beta) x += ep.C[off];
+                        if (ep.act == 1) x = fmaxf(x, 0.0f);
+                        if (ep.relu_mask && !(ep.relu_mask[off] > 0.0f)) x = 0.0f;
+                        if (ep.round_out) x = tf32_rn(x);
+                        ep.C[off] = x;
                     }
                 }
             }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -254,8 +239,27 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is fetched through the runtime so that libbdetr.so has no link-time dependency on
+// libcuda.so.1 (the library must also load on GPU-less build hosts).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
 static bool encode_map(CUtensorMap *map, const float *base, int rows, int cols, int ld, int box_cols, int box_rows, bool mn_major)
 {
+    EncodeTiledFn cuTensorMapEncodeTiled = encode_tiled_fn();
+    if (!cuTensorMapEncodeTiled) return false;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
@@ -266,8 +270,8 @@ static bool encode_map(CUtensorMap *map, const float *base, int rows, int cols, 
     return r == CUDA_SUCCESS;
 }
 
-template <int BN>
-static size_t umma_smem_bytes() { return (size_t)UM_STAGES * (UM_BM * UM_BK * 4 + BN * UM_BK * 4) + (2 * UM_STAGES + 1) * 8 + 16 + 1024; }
+template <int BN, int STAGES>
+static size_t umma_smem_bytes() { return (size_t)STAGES * (UM_BM * UM_BK * 4 + BN * UM_BK * 4) + (2 * STAGES + 1) * 8 + 16 + 4 * 32 * 33 * 4 + 1024; }
 
 bool umma_gemm_eligible(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB, int ldc)
 {
@@ -279,25 +283,28 @@ bool umma_gemm_eligible(int M, int N, int K, const float *A, int lda, bool TA, c
 template <int BN, bool A_MN, bool B_MN>
 static int launch_umma_inst(dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const UmmaEpilogue &ep, cudaStream_t s)
 {
+    constexpr int STAGES = BN == 64 ? 3 : 4;        // BN=64: 89 KB per CTA -> two CTAs per SM overlap load and epilogue
     static bool optin = false;
-    const size_t smem = umma_smem_bytes<BN>();
+    const size_t smem = umma_smem_bytes<BN, STAGES>();
     if (!optin) {
-        BDETR_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BDETR_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<BN, STAGES, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         optin = true;
     }
-    gemm_umma_kernel<BN, A_MN, B_MN><<<grid, UM_THREADS, smem, s>>>(ma, mb, ep);
+    gemm_umma_kernel<BN, STAGES, A_MN, B_MN><<<grid, UM_THREADS, smem, s>>>(ma, mb, ep);
     BDETR_CHECK_LAUNCH("gemm_umma_kernel");
     return BDETR_OK;
 }
 
 // Same contract as launch_gemm (gemm_simt.cu).  TA: A stored [K,M]; TB: B stored [N,K].
 int launch_gemm_umma(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB,
-                     const float *bias, int act, const float *relu_mask, int beta, float *C, int ldc, cudaStream_t s)
+                     const float *bias, int act, const float *relu_mask, int beta, int round_out, float *C, int ldc,
+                     cudaStream_t s)
 {
     // operand majors: A K-major when stored [M,K]; MN-major when stored [K,M].  B K-major when stored [N,K];
     // MN-major when stored [K,N] (Keras kernels and dY).
     const bool A_MN = TA, B_MN = !TB;
-    const int BN = (N >= 128) ? 128 : 64;
+    // 128x128 tiles unless they would leave most SMs idle; 128x64 tiles run two CTAs per SM
+    const int BN = (N >= 128 && ceil_div(M, UM_BM) * ceil_div(N, 128) >= 120) ? 128 : 64;
     CUtensorMap ma, mb;
     bool ok;
     if (!A_MN) ok = encode_map(&ma, A, M, K, lda, UM_BK, UM_BM, false);          // [M rows, K cols], box {32 k, 128 m}
@@ -307,11 +314,11 @@ int launch_gemm_umma(int M, int N, int K, const float *A, int lda, bool TA, cons
     BDETR_REQUIRE(ok, BDETR_E_CUDA, "cuTensorMapEncodeTiled failed");
 
     UmmaEpilogue ep;
-    ep.M = M; ep.N = N; ep.bias = bias; ep.act = act; ep.relu_mask = relu_mask; ep.beta = beta; ep.C = C; ep.ldc = ldc;
+    ep.M = M; ep.N = N; ep.bias = bias; ep.act = act; ep.relu_mask = relu_mask; ep.beta = beta; ep.round_out = round_out; ep.C = C; ep.ldc = ldc;
     ep.num_kb = ceil_div(K, UM_BK);
     const int tiles = ceil_div(M, UM_BM) * ceil_div(N, BN);
     int splits = 1;
-    if (act == 0 && relu_mask == nullptr && tiles < 74 && ep.num_kb >= 16) splits = min(ep.num_kb / 4, max(1, 148 / tiles));
+    if (act == 0 && relu_mask == nullptr && !round_out && tiles < 74 && ep.num_kb >= 16) splits = min(ep.num_kb / 4, max(1, 296 / tiles));
     ep.kb_per_split = ceil_div(ep.num_kb, splits);
     splits = ceil_div(ep.num_kb, ep.kb_per_split);
     ep.atomic_out = splits > 1;

@@ -9,42 +9,47 @@ int current_mode();
 // C[M,N] = (beta ? C : 0) + op(A)[M,K] @ op(B)[K,N] (+bias[n]) ; act 1 = relu ;
 // relu_mask != NULL: C[m,n] = 0 where relu_mask[m*ldc+n] <= 0 (backward of relu, applied last).
 // TA: A stored [K,M] (lda = M-stride of k rows); TB: B stored [N,K].
+// round_out: store the result rounded to tf32 (tensor-core mode, outputs that feed another GEMM).
 int launch_gemm(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB,
-                const float *bias, int act, const float *relu_mask, int beta, float *C, int ldc, cudaStream_t s);
+                const float *bias, int act, const float *relu_mask, int beta, int round_out, float *C, int ldc,
+                cudaStream_t s);
 
 // tcgen05 / TMA / TMEM tensor-core path (gemm_umma.cu), same contract as launch_gemm
 bool umma_gemm_eligible(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB, int ldc);
 int launch_gemm_umma(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB,
-                     const float *bias, int act, const float *relu_mask, int beta, float *C, int ldc, cudaStream_t s);
+                     const float *bias, int act, const float *relu_mask, int beta, int round_out, float *C, int ldc,
+                     cudaStream_t s);
 
 // dst[n] += sum_m src[m, n]
 int launch_colsum_acc(int M, int N, const float *src, float *dst, cudaStream_t s);
 
 int launch_attention_fwd(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
-                         float *o, float *lse, cudaStream_t s);
+                         float *o, float *lse, int round_out, cudaStream_t s);
 int launch_attention_bwd(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
                          const float *o, const float *lse, const float *d_o, float *delta,
-                         float *d_qp, float *d_kp, float *d_vp, cudaStream_t s);
+                         float *d_qp, float *d_kp, float *d_vp, int round_out, cudaStream_t s);
 
 // z = resid + dropout(z) (in place), out = LN(z); saves mean/rstd.
 int launch_res_ln_fwd(int M, int D, const float *resid, float *z, const float *gamma, const float *beta, float eps,
-                      float rate, uint32_t key, float *out, float *mean, float *rstd, cudaStream_t s);
+                      float rate, uint32_t key, float *out, float *mean, float *rstd, int round_out, cudaStream_t s);
 // d_z -> d_resid (overwrite/accumulate) and d_a = dropout'(d_z); g_gamma/g_beta accumulated.
 int launch_res_ln_bwd(int M, int D, const float *d_out, const float *z, const float *mean, const float *rstd,
                       const float *gamma, float rate, uint32_t key, float *d_resid, int acc_resid, float *d_a,
-                      float *g_gamma, float *g_beta, cudaStream_t s);
+                      float *g_gamma, float *g_beta, int round_out, cudaStream_t s);
 
-int launch_add_rows_fwd(int B, int L, int D, const float *x, const float *pos, float *out, cudaStream_t s);
+int launch_add_rows_fwd(int B, int L, int D, const float *x, const float *pos, float *out, int round_out, cudaStream_t s);
 int launch_batch_sum_acc(int B, int L, int D, const float *src, float *dst, cudaStream_t s);
-int launch_tile_rows(int B, int L, int D, const float *src, float *dst, cudaStream_t s);
+int launch_tile_rows(int B, int L, int D, const float *src, float *dst, int round_out, cudaStream_t s);
+int launch_round_tf32(size_t n, const float *src, float *dst, cudaStream_t s);
 int launch_accumulate(size_t n, const float *x, float *y, cudaStream_t s);
 
+// acc: [2*Dh] scratch for the cross-CTA column sums
 int launch_bn_fwd(int M, int Dh, const float *h, const float *gamma, const float *beta, float *moving_mean,
-                  float *moving_var, float eps, float momentum, int training, float *hn, float *mean, float *rstd,
+                  float *moving_var, float eps, float momentum, int training, float *acc, float *hn, float *mean, float *rstd,
                   cudaStream_t s);
 // d_h = relu'(h) * BN_backward(d_hn); g_gamma/g_beta accumulated
 int launch_bn_relu_bwd(int M, int Dh, const float *h, const float *d_hn, const float *gamma, const float *mean,
-                       const float *rstd, float *d_h, float *g_gamma, float *g_beta, cudaStream_t s);
+                       const float *rstd, float *acc, float *d_h, float *g_gamma, float *g_beta, int round_out, cudaStream_t s);
 // act in place on logits [M,N]; cum = (init ? 0 : cum) + mult*act
 int launch_head_act_fwd(int M, int N, int kind, float mult, float *act, float *cum, int cum_init, cudaStream_t s);
 int launch_head_act_bwd(int M, int N, int kind, float mult, const float *act, const float *d_cum, float *d_logits,

@@ -15,7 +15,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 res_ln_fwd_kernel(int M, const float *__restrict__ resid, float *__restrict__ z, const float *__restrict__ gamma,
                   const float *__restrict__ beta, float eps, float keep_scale, uint32_t thresh, uint32_t key,
-                  float *__restrict__ out, float *__restrict__ mean_o, float *__restrict__ rstd_o)
+                  float *__restrict__ out, float *__restrict__ mean_o, float *__restrict__ rstd_o, int round_out)
 {
     constexpr int D = NV * 128;
     const int lane = threadIdx.x & 31;
@@ -52,6 +52,7 @@ res_ln_fwd_kernel(int M, const float *__restrict__ resid, float *__restrict__ z,
         float4 y;
         y.x = (v[4 * k] - mean) * rstd * g.x + bt.x; y.y = (v[4 * k + 1] - mean) * rstd * g.y + bt.y;
         y.z = (v[4 * k + 2] - mean) * rstd * g.z + bt.z; y.w = (v[4 * k + 3] - mean) * rstd * g.w + bt.w;
+        if (round_out) { y.x = tf32_rn(y.x); y.y = tf32_rn(y.y); y.z = tf32_rn(y.z); y.w = tf32_rn(y.w); }
         *reinterpret_cast<float4 *>(out + (size_t)row * D + col) = y;
     }
     if (lane == 0) { mean_o[row] = mean; rstd_o[row] = rstd; }
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(256)
 res_ln_bwd_kernel(int M, const float *__restrict__ d_out, const float *__restrict__ z, const float *__restrict__ mean_i,
                   const float *__restrict__ rstd_i, const float *__restrict__ gamma, float keep_scale, uint32_t thresh,
                   uint32_t key, float *__restrict__ d_resid, int acc_resid, float *__restrict__ d_a,
-                  float *__restrict__ g_gamma, float *__restrict__ g_beta)
+                  float *__restrict__ g_gamma, float *__restrict__ g_beta, int round_out)
 {
     constexpr int D = NV * 128;
     __shared__ float red_g[8][D + 4];
@@ -108,6 +109,7 @@ res_ln_bwd_kernel(int M, const float *__restrict__ d_out, const float *__restric
                 const int idx = 4 * k + e;
                 dz[e] = rstd * (dy[idx] - s1 - xh[idx] * s2);
                 da[e] = thresh ? (dropout_keep((uint32_t)(off + e), key, thresh) ? dz[e] * keep_scale : 0.0f) : dz[e];
+                da[e] = maybe_tf32(da[e], round_out);
             }
             *reinterpret_cast<float4 *>(d_a + off) = make_float4(da[0], da[1], da[2], da[3]);
             if (d_resid) {
@@ -135,30 +137,30 @@ res_ln_bwd_kernel(int M, const float *__restrict__ d_out, const float *__restric
 }
 
 int launch_res_ln_fwd(int M, int D, const float *resid, float *z, const float *gamma, const float *beta, float eps,
-                      float rate, uint32_t key, float *out, float *mean, float *rstd, cudaStream_t s)
+                      float rate, uint32_t key, float *out, float *mean, float *rstd, int round_out, cudaStream_t s)
 {
     BDETR_REQUIRE(M > 0 && (D == 128 || D == 256 || D == 512), BDETR_E_UNSUPPORTED, "LayerNorm width must be 128, 256 or 512");
     const uint32_t thresh = dropout_threshold(rate);
     const float ks = 1.0f / (1.0f - rate);
     const int grid = ceil_div(M, 8);
-    if (D == 128) res_ln_fwd_kernel<1><<<grid, 256, 0, s>>>(M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd);
-    else if (D == 256) res_ln_fwd_kernel<2><<<grid, 256, 0, s>>>(M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd);
-    else res_ln_fwd_kernel<4><<<grid, 256, 0, s>>>(M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd);
+    if (D == 128) res_ln_fwd_kernel<1><<<grid, 256, 0, s>>>(M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd, round_out);
+    else if (D == 256) res_ln_fwd_kernel<2><<<grid, 256, 0, s>>>(M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd, round_out);
+    else res_ln_fwd_kernel<4><<<grid, 256, 0, s>>>(M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd, round_out);
     BDETR_CHECK_LAUNCH("res_ln_fwd_kernel");
     return BDETR_OK;
 }
 
 int launch_res_ln_bwd(int M, int D, const float *d_out, const float *z, const float *mean, const float *rstd,
                       const float *gamma, float rate, uint32_t key, float *d_resid, int acc_resid, float *d_a,
-                      float *g_gamma, float *g_beta, cudaStream_t s)
+                      float *g_gamma, float *g_beta, int round_out, cudaStream_t s)
 {
     BDETR_REQUIRE(M > 0 && (D == 128 || D == 256 || D == 512), BDETR_E_UNSUPPORTED, "LayerNorm width must be 128, 256 or 512");
     const uint32_t thresh = dropout_threshold(rate);
     const float ks = 1.0f / (1.0f - rate);
     const int grid = min(ceil_div(M, 8), 296);
-    if (D == 128) res_ln_bwd_kernel<1><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta);
-    else if (D == 256) res_ln_bwd_kernel<2><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta);
-    else res_ln_bwd_kernel<4><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta);
+    if (D == 128) res_ln_bwd_kernel<1><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, round_out);
+    else if (D == 256) res_ln_bwd_kernel<2><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, round_out);
+    else res_ln_bwd_kernel<4><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, round_out);
     BDETR_CHECK_LAUNCH("res_ln_bwd_kernel");
     return BDETR_OK;
 }
@@ -166,12 +168,21 @@ int launch_res_ln_bwd(int M, int D, const float *d_out, const float *z, const fl
 // ------------------------------------------------------------------------------------------
 // elementwise helpers
 // ------------------------------------------------------------------------------------------
-__global__ void add_rows_fwd_kernel(size_t n4, size_t ld4, const float4 *__restrict__ x, const float4 *__restrict__ pos, float4 *__restrict__ out)
+__device__ __forceinline__ float4 round4(float4 v, int on)
+{
+    if (on) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
+    return v;
+}
+__global__ void add_rows_fwd_kernel(size_t n4, size_t ld4, const float4 *__restrict__ x, const float4 *__restrict__ pos, float4 *__restrict__ out, int round_out)
 {
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
         const float4 a = x[e], p = pos[e % ld4];
-        out[e] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+        out[e] = round4(make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w), round_out);
     }
+}
+__global__ void round_tf32_kernel(size_t n, const float *__restrict__ src, float *__restrict__ dst)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) dst[e] = tf32_rn(src[e]);
 }
 __global__ void batch_sum_acc_kernel(int B, size_t ld4, const float4 *__restrict__ src, float4 *__restrict__ dst)
 {
@@ -181,9 +192,9 @@ __global__ void batch_sum_acc_kernel(int B, size_t ld4, const float4 *__restrict
         dst[e] = a;
     }
 }
-__global__ void tile_rows_kernel(size_t n4, size_t ld4, const float4 *__restrict__ src, float4 *__restrict__ dst)
+__global__ void tile_rows_kernel(size_t n4, size_t ld4, const float4 *__restrict__ src, float4 *__restrict__ dst, int round_out)
 {
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) dst[e] = src[e % ld4];
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) dst[e] = round4(src[e % ld4], round_out);
 }
 __global__ void accumulate_kernel(size_t n, const float *__restrict__ x, float *__restrict__ y)
 {
@@ -192,11 +203,11 @@ __global__ void accumulate_kernel(size_t n, const float *__restrict__ x, float *
 
 static inline int ew_grid(size_t n) { size_t g = (n + 255) / 256; return (int)(g < 148 * 8 ? (g ? g : 1) : 148 * 8); }
 
-int launch_add_rows_fwd(int B, int L, int D, const float *x, const float *pos, float *out, cudaStream_t s)
+int launch_add_rows_fwd(int B, int L, int D, const float *x, const float *pos, float *out, int round_out, cudaStream_t s)
 {
     BDETR_REQUIRE(B > 0 && L > 0 && D > 0 && D % 4 == 0, BDETR_E_BAD_SHAPE, "D must be a multiple of 4");
     const size_t ld4 = (size_t)L * D / 4, n4 = ld4 * B;
-    add_rows_fwd_kernel<<<ew_grid(n4), 256, 0, s>>>(n4, ld4, (const float4 *)x, (const float4 *)pos, (float4 *)out);
+    add_rows_fwd_kernel<<<ew_grid(n4), 256, 0, s>>>(n4, ld4, (const float4 *)x, (const float4 *)pos, (float4 *)out, round_out);
     BDETR_CHECK_LAUNCH("add_rows_fwd_kernel");
     return BDETR_OK;
 }
@@ -208,12 +219,19 @@ int launch_batch_sum_acc(int B, int L, int D, const float *src, float *dst, cuda
     BDETR_CHECK_LAUNCH("batch_sum_acc_kernel");
     return BDETR_OK;
 }
-int launch_tile_rows(int B, int L, int D, const float *src, float *dst, cudaStream_t s)
+int launch_tile_rows(int B, int L, int D, const float *src, float *dst, int round_out, cudaStream_t s)
 {
     BDETR_REQUIRE(B > 0 && L > 0 && D > 0 && D % 4 == 0, BDETR_E_BAD_SHAPE, "D must be a multiple of 4");
     const size_t ld4 = (size_t)L * D / 4, n4 = ld4 * B;
-    tile_rows_kernel<<<ew_grid(n4), 256, 0, s>>>(n4, ld4, (const float4 *)src, (float4 *)dst);
+    tile_rows_kernel<<<ew_grid(n4), 256, 0, s>>>(n4, ld4, (const float4 *)src, (float4 *)dst, round_out);
     BDETR_CHECK_LAUNCH("tile_rows_kernel");
+    return BDETR_OK;
+}
+int launch_round_tf32(size_t n, const float *src, float *dst, cudaStream_t s)
+{
+    BDETR_REQUIRE(n > 0 && src && dst, BDETR_E_BAD_SHAPE, "bad round arguments");
+    round_tf32_kernel<<<ew_grid(n), 256, 0, s>>>(n, src, dst);
+    BDETR_CHECK_LAUNCH("round_tf32_kernel");
     return BDETR_OK;
 }
 int launch_accumulate(size_t n, const float *x, float *y, cudaStream_t s)
@@ -240,81 +258,118 @@ __device__ __forceinline__ float col_reduce8(float v, float (*red)[33])
     return t;
 }
 
+constexpr int BN_ROWS = 128;     // rows per CTA: grid = (Dh/32, M/128) so the whole chip takes part
+
+// acc[0:Dh] += sum_m (h - pivot), acc[Dh:2Dh] += sum_m (h - pivot)^2, pivot = h[0, c] (kills the cancellation)
 __global__ void __launch_bounds__(256)
-bn_fwd_kernel(int M, int Dh, const float *__restrict__ h, const float *__restrict__ gamma, const float *__restrict__ beta,
-              float *__restrict__ moving_mean, float *__restrict__ moving_var, float eps, float momentum, int training,
-              float *__restrict__ hn, float *__restrict__ mean_o, float *__restrict__ rstd_o)
+bn_stats_kernel(int M, int Dh, const float *__restrict__ h, float *__restrict__ acc)
 {
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
     const bool live = c < Dh;
+    const int m0 = blockIdx.y * BN_ROWS, m1 = min(M, m0 + BN_ROWS);
+    const float pivot = live ? h[c] : 0.0f;
+    float s1 = 0.0f, s2 = 0.0f;
+    if (live) for (int m = m0 + r; m < m1; m += 8) { const float d = h[(size_t)m * Dh + c] - pivot; s1 += d; s2 = fmaf(d, d, s2); }
+    s1 = col_reduce8(s1, red);
+    s2 = col_reduce8(s2, red);
+    if (live && r == 0) { atomicAdd(&acc[c], s1); atomicAdd(&acc[Dh + c], s2); }
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(int M, int Dh, const float *__restrict__ h, const float *__restrict__ gamma, const float *__restrict__ beta,
+                float *__restrict__ moving_mean, float *__restrict__ moving_var, float eps, float momentum, int training,
+                const float *__restrict__ acc, float *__restrict__ hn, float *__restrict__ mean_o, float *__restrict__ rstd_o)
+{
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+    if (c >= Dh) return;
     float mean, var;
     if (training) {
-        float s = 0.0f;
-        if (live) for (int m = r; m < M; m += 8) s += h[(size_t)m * Dh + c];
-        mean = col_reduce8(s, red) / (float)M;
-        float q = 0.0f;
-        if (live) for (int m = r; m < M; m += 8) { const float d = h[(size_t)m * Dh + c] - mean; q = fmaf(d, d, q); }
-        var = col_reduce8(q, red) / (float)M;
-        if (live && r == 0) {
+        const float a1 = acc[c] / (float)M, a2 = acc[Dh + c] / (float)M;
+        mean = h[c] + a1;
+        var = fmaxf(a2 - a1 * a1, 0.0f);
+        if (blockIdx.y == 0 && r == 0) {
             moving_mean[c] = moving_mean[c] * momentum + mean * (1.0f - momentum);
             moving_var[c] = moving_var[c] * momentum + var * (1.0f - momentum);
         }
     } else {
-        mean = live ? moving_mean[c] : 0.0f;
-        var = live ? moving_var[c] : 1.0f;
+        mean = moving_mean[c];
+        var = moving_var[c];
     }
     const float rstd = rsqrtf(var + eps);
-    if (!live) return;
-    if (r == 0) { mean_o[c] = mean; rstd_o[c] = rstd; }
+    if (blockIdx.y == 0 && r == 0) { mean_o[c] = mean; rstd_o[c] = rstd; }
     const float g = gamma[c], b = beta[c];
-    for (int m = r; m < M; m += 8) hn[(size_t)m * Dh + c] = (h[(size_t)m * Dh + c] - mean) * rstd * g + b;
+    const int m0 = blockIdx.y * BN_ROWS, m1 = min(M, m0 + BN_ROWS);
+    for (int m = m0 + r; m < m1; m += 8) hn[(size_t)m * Dh + c] = (h[(size_t)m * Dh + c] - mean) * rstd * g + b;
 }
 
+// acc[0:Dh] += sum dy, acc[Dh:2Dh] += sum dy * xhat
 __global__ void __launch_bounds__(256)
-bn_relu_bwd_kernel(int M, int Dh, const float *__restrict__ h, const float *__restrict__ d_hn, const float *__restrict__ gamma,
-                   const float *__restrict__ mean_i, const float *__restrict__ rstd_i, float *__restrict__ d_h,
-                   float *__restrict__ g_gamma, float *__restrict__ g_beta)
+bn_bwd_stats_kernel(int M, int Dh, const float *__restrict__ h, const float *__restrict__ d_hn, const float *__restrict__ mean_i,
+                    const float *__restrict__ rstd_i, float *__restrict__ acc)
 {
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
     const bool live = c < Dh;
-    const float mean = live ? mean_i[c] : 0.0f, rstd = live ? rstd_i[c] : 0.0f, g = live ? gamma[c] : 0.0f;
+    const int m0 = blockIdx.y * BN_ROWS, m1 = min(M, m0 + BN_ROWS);
+    const float mean = live ? mean_i[c] : 0.0f, rstd = live ? rstd_i[c] : 0.0f;
     float s1 = 0.0f, s2 = 0.0f;
-    if (live) for (int m = r; m < M; m += 8) {
+    if (live) for (int m = m0 + r; m < m1; m += 8) {
         const float dy = d_hn[(size_t)m * Dh + c];
         s1 += dy;
         s2 = fmaf(dy, (h[(size_t)m * Dh + c] - mean) * rstd, s2);
     }
-    s1 = col_reduce8(s1, red);      // sum dy        (= d beta)
-    s2 = col_reduce8(s2, red);      // sum dy * xhat (= d gamma)
-    if (!live) return;
-    if (r == 0) { g_gamma[c] += s2; g_beta[c] += s1; }
+    s1 = col_reduce8(s1, red);
+    s2 = col_reduce8(s2, red);
+    if (live && r == 0) { atomicAdd(&acc[c], s1); atomicAdd(&acc[Dh + c], s2); }
+}
+
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_apply_kernel(int M, int Dh, const float *__restrict__ h, const float *__restrict__ d_hn, const float *__restrict__ gamma,
+                         const float *__restrict__ mean_i, const float *__restrict__ rstd_i, const float *__restrict__ acc,
+                         float *__restrict__ d_h, float *__restrict__ g_gamma, float *__restrict__ g_beta, int round_out)
+{
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+    if (c >= Dh) return;
+    const float mean = mean_i[c], rstd = rstd_i[c], g = gamma[c];
+    const float s1 = acc[c], s2 = acc[Dh + c];
+    if (blockIdx.y == 0 && r == 0) { g_gamma[c] += s2; g_beta[c] += s1; }
     const float invM = 1.0f / (float)M;
-    for (int m = r; m < M; m += 8) {
+    const int m0 = blockIdx.y * BN_ROWS, m1 = min(M, m0 + BN_ROWS);
+    for (int m = m0 + r; m < m1; m += 8) {
         const size_t off = (size_t)m * Dh + c;
         const float hv = h[off];
         const float xh = (hv - mean) * rstd;
         const float dx = g * rstd * (d_hn[off] - s1 * invM - xh * s2 * invM);
-        d_h[off] = hv > 0.0f ? dx : 0.0f;           // ReLU backward (h is the post-ReLU activation)
+        d_h[off] = hv > 0.0f ? maybe_tf32(dx, round_out) : 0.0f;      // ReLU backward (h is the post-ReLU activation)
     }
 }
 
 int launch_bn_fwd(int M, int Dh, const float *h, const float *gamma, const float *beta, float *moving_mean,
-                  float *moving_var, float eps, float momentum, int training, float *hn, float *mean, float *rstd,
+                  float *moving_var, float eps, float momentum, int training, float *acc, float *hn, float *mean, float *rstd,
                   cudaStream_t s)
 {
-    BDETR_REQUIRE(M > 0 && Dh > 0, BDETR_E_BAD_SHAPE, "bad BatchNorm shape");
-    bn_fwd_kernel<<<ceil_div(Dh, 32), 256, 0, s>>>(M, Dh, h, gamma, beta, moving_mean, moving_var, eps, momentum, training, hn, mean, rstd);
-    BDETR_CHECK_LAUNCH("bn_fwd_kernel");
+    BDETR_REQUIRE(M > 0 && Dh > 0 && acc, BDETR_E_BAD_SHAPE, "bad BatchNorm arguments");
+    dim3 grid(ceil_div(Dh, 32), ceil_div(M, BN_ROWS));
+    if (training) {
+        BDETR_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 2 * Dh, s));
+        bn_stats_kernel<<<grid, 256, 0, s>>>(M, Dh, h, acc);
+        BDETR_CHECK_LAUNCH("bn_stats_kernel");
+    }
+    bn_apply_kernel<<<grid, 256, 0, s>>>(M, Dh, h, gamma, beta, moving_mean, moving_var, eps, momentum, training, acc, hn, mean, rstd);
+    BDETR_CHECK_LAUNCH("bn_apply_kernel");
     return BDETR_OK;
 }
 int launch_bn_relu_bwd(int M, int Dh, const float *h, const float *d_hn, const float *gamma, const float *mean,
-                       const float *rstd, float *d_h, float *g_gamma, float *g_beta, cudaStream_t s)
+                       const float *rstd, float *acc, float *d_h, float *g_gamma, float *g_beta, int round_out, cudaStream_t s)
 {
-    BDETR_REQUIRE(M > 0 && Dh > 0, BDETR_E_BAD_SHAPE, "bad BatchNorm shape");
-    bn_relu_bwd_kernel<<<ceil_div(Dh, 32), 256, 0, s>>>(M, Dh, h, d_hn, gamma, mean, rstd, d_h, g_gamma, g_beta);
-    BDETR_CHECK_LAUNCH("bn_relu_bwd_kernel");
+    BDETR_REQUIRE(M > 0 && Dh > 0 && acc, BDETR_E_BAD_SHAPE, "bad BatchNorm arguments");
+    dim3 grid(ceil_div(Dh, 32), ceil_div(M, BN_ROWS));
+    BDETR_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 2 * Dh, s));
+    bn_bwd_stats_kernel<<<grid, 256, 0, s>>>(M, Dh, h, d_hn, mean, rstd, acc);
+    BDETR_CHECK_LAUNCH("bn_bwd_stats_kernel");
+    bn_relu_bwd_apply_kernel<<<grid, 256, 0, s>>>(M, Dh, h, d_hn, gamma, mean, rstd, acc, d_h, g_gamma, g_beta, round_out);
+    BDETR_CHECK_LAUNCH("bn_relu_bwd_apply_kernel");
     return BDETR_OK;
 }
 

@@ -6,18 +6,22 @@ using namespace bdetr;
 #define API extern "C" __attribute__((visibility("default")))
 #define TRY(x) do { int rc__ = (x); if (rc__ != BDETR_OK) return rc__; } while (0)
 
+// Tensor-core mode: every tensor that feeds a tcgen05 GEMM is stored rounded to tf32 (round-to-nearest) by
+// its producer, so the MMA's operand truncation is exact.  `rnd` below is that flag.
+static inline int tc_mode() { return current_mode() == BDETR_MODE_TF32 ? 1 : 0; }
+
 // y = x @ W + b, W is a Keras kernel [K,N]
-static int linear_fwd(int M, int N, int K, const float *x, const float *W, const float *b, int act, float *y, cudaStream_t s)
+static int linear_fwd(int M, int N, int K, const float *x, const float *W, const float *b, int act, float *y, int rnd, cudaStream_t s)
 {
-    return launch_gemm(M, N, K, x, K, false, W, N, false, b, act, nullptr, 0, y, N, s);
+    return launch_gemm(M, N, K, x, K, false, W, N, false, b, act, nullptr, 0, rnd, y, N, s);
 }
 // gW += x^T dy ; gb += colsum(dy) ; dx (=|+=) dy W^T (optionally masked by relu_mask afterwards)
 static int linear_bwd(int M, int N, int K, const float *x, const float *W, const float *dy, float *gW, float *gb,
-                      float *dx, int acc_dx, const float *relu_mask, cudaStream_t s)
+                      float *dx, int acc_dx, const float *relu_mask, int rnd_dx, cudaStream_t s)
 {
-    if (gW) TRY(launch_gemm(K, N, M, x, K, true, dy, N, false, nullptr, 0, nullptr, 1, gW, N, s));
+    if (gW) TRY(launch_gemm(K, N, M, x, K, true, dy, N, false, nullptr, 0, nullptr, 1, 0, gW, N, s));
     if (gb) TRY(launch_colsum_acc(M, N, dy, gb, s));
-    if (dx) TRY(launch_gemm(M, K, N, dy, N, false, W, N, true, nullptr, 0, relu_mask, acc_dx, dx, K, s));
+    if (dx) TRY(launch_gemm(M, K, N, dy, N, false, W, N, true, nullptr, 0, relu_mask, acc_dx, rnd_dx, dx, K, s));
     return BDETR_OK;
 }
 
@@ -25,7 +29,7 @@ API int bdetr_gemm(int M, int N, int K, const float *A, int transA, const float 
                    const float *bias, int act, int beta, float *C, void *stream)
 {
     return launch_gemm(M, N, K, A, transA ? M : K, transA != 0, Bm, transB ? K : N, transB != 0, bias, act, nullptr,
-                       beta, C, N, as_stream(stream));
+                       beta, 0, C, N, as_stream(stream));
 }
 
 API int bdetr_attention_block_fwd(int B, int Lq, int Lk, int D, int H,
@@ -38,13 +42,14 @@ API int bdetr_attention_block_fwd(int B, int Lq, int Lk, int D, int H,
     BDETR_REQUIRE(sv->qp && sv->kp && sv->vp && sv->o && sv->lse && sv->z && sv->mean && sv->rstd, BDETR_E_NULL, "null saved buffer");
     cudaStream_t s = as_stream(stream);
     const int Mq = B * Lq, Mk = B * Lk;
-    TRY(linear_fwd(Mq, D, D, query, w->wq, w->bq, 0, sv->qp, s));
-    TRY(linear_fwd(Mk, D, D, key, w->wk, w->bk, 0, sv->kp, s));
-    TRY(linear_fwd(Mk, D, D, value, w->wv, w->bv, 0, sv->vp, s));
-    TRY(launch_attention_fwd(B, H, Lq, Lk, D / H, sv->qp, sv->kp, sv->vp, sv->o, sv->lse, s));
+    const int rnd = tc_mode();
+    TRY(linear_fwd(Mq, D, D, query, w->wq, w->bq, 0, sv->qp, 0, s));
+    TRY(linear_fwd(Mk, D, D, key, w->wk, w->bk, 0, sv->kp, 0, s));
+    TRY(linear_fwd(Mk, D, D, value, w->wv, w->bv, 0, sv->vp, 0, s));
+    TRY(launch_attention_fwd(B, H, Lq, Lk, D / H, sv->qp, sv->kp, sv->vp, sv->o, sv->lse, rnd, s));
     // sv->o is [B,H,Lq,d]; read back as [B*Lq, D] with no permute (reference transformers.py:100)
-    TRY(linear_fwd(Mq, D, D, sv->o, w->wo, w->bo, 0, sv->z, s));
-    TRY(launch_res_ln_fwd(Mq, D, query, sv->z, w->ln_gamma, w->ln_beta, ln_eps, dropout_rate, dropout_key, out, sv->mean, sv->rstd, s));
+    TRY(linear_fwd(Mq, D, D, sv->o, w->wo, w->bo, 0, sv->z, 0, s));
+    TRY(launch_res_ln_fwd(Mq, D, query, sv->z, w->ln_gamma, w->ln_beta, ln_eps, dropout_rate, dropout_key, out, sv->mean, sv->rstd, rnd, s));
     return BDETR_OK;
 }
 
@@ -61,15 +66,16 @@ API int bdetr_attention_block_bwd(int B, int Lq, int Lk, int D, int H,
     cudaStream_t s = as_stream(stream);
     const int Mq = B * Lq, Mk = B * Lk;
     // LayerNorm + residual + dropout: residual gradient goes straight to d_query
+    const int rnd = tc_mode();
     TRY(launch_res_ln_bwd(Mq, D, d_out, sv->z, sv->mean, sv->rstd, w->ln_gamma, dropout_rate, dropout_key,
-                          d_query, acc_flags & 1, sc->d_z, gw->ln_gamma, gw->ln_beta, s));
+                          d_query, acc_flags & 1, sc->d_z, gw->ln_gamma, gw->ln_beta, rnd, s));
     // output projection
-    TRY(linear_bwd(Mq, D, D, sv->o, w->wo, sc->d_z, gw->wo, gw->bo, sc->d_o, 0, nullptr, s));
+    TRY(linear_bwd(Mq, D, D, sv->o, w->wo, sc->d_z, gw->wo, gw->bo, sc->d_o, 0, nullptr, 0, s));
     TRY(launch_attention_bwd(B, H, Lq, Lk, D / H, sv->qp, sv->kp, sv->vp, sv->o, sv->lse, sc->d_o, sc->delta,
-                             sc->d_qp, sc->d_kp, sc->d_vp, s));
-    TRY(linear_bwd(Mq, D, D, query, w->wq, sc->d_qp, gw->wq, gw->bq, d_query, 1, nullptr, s));
-    TRY(linear_bwd(Mk, D, D, key, w->wk, sc->d_kp, gw->wk, gw->bk, d_key, (acc_flags >> 1) & 1, nullptr, s));
-    TRY(linear_bwd(Mk, D, D, value, w->wv, sc->d_vp, gw->wv, gw->bv, d_value, (acc_flags >> 2) & 1, nullptr, s));
+                             sc->d_qp, sc->d_kp, sc->d_vp, rnd, s));
+    TRY(linear_bwd(Mq, D, D, query, w->wq, sc->d_qp, gw->wq, gw->bq, d_query, 1, nullptr, 0, s));
+    TRY(linear_bwd(Mk, D, D, key, w->wk, sc->d_kp, gw->wk, gw->bk, d_key, (acc_flags >> 1) & 1, nullptr, 0, s));
+    TRY(linear_bwd(Mk, D, D, value, w->wv, sc->d_vp, gw->wv, gw->bv, d_value, (acc_flags >> 2) & 1, nullptr, 0, s));
     return BDETR_OK;
 }
 
@@ -80,9 +86,10 @@ API int bdetr_ffn_block_fwd(int M, int D, const float *x, const bdetr_ffn_params
     BDETR_REQUIRE(M > 0 && D > 0, BDETR_E_BAD_SHAPE, "bad shape");
     BDETR_REQUIRE(x && w && out && sv && sv->h && sv->z && sv->mean && sv->rstd, BDETR_E_NULL, "null pointer");
     cudaStream_t s = as_stream(stream);
-    TRY(linear_fwd(M, D, D, x, w->w1, w->b1, 1, sv->h, s));
-    TRY(linear_fwd(M, D, D, sv->h, w->w2, w->b2, 0, sv->z, s));
-    TRY(launch_res_ln_fwd(M, D, x, sv->z, w->ln_gamma, w->ln_beta, ln_eps, dropout_rate, dropout_key, out, sv->mean, sv->rstd, s));
+    const int rnd = tc_mode();
+    TRY(linear_fwd(M, D, D, x, w->w1, w->b1, 1, sv->h, rnd, s));
+    TRY(linear_fwd(M, D, D, sv->h, w->w2, w->b2, 0, sv->z, 0, s));
+    TRY(launch_res_ln_fwd(M, D, x, sv->z, w->ln_gamma, w->ln_beta, ln_eps, dropout_rate, dropout_key, out, sv->mean, sv->rstd, rnd, s));
     return BDETR_OK;
 }
 
@@ -95,18 +102,19 @@ API int bdetr_ffn_block_bwd(int M, int D, const float *x, const bdetr_ffn_params
     BDETR_REQUIRE(M > 0 && D > 0, BDETR_E_BAD_SHAPE, "bad shape");
     BDETR_REQUIRE(x && w && sv && d_out && d_x && gw && sc && sc->d_z && sc->d_h, BDETR_E_NULL, "null pointer");
     cudaStream_t s = as_stream(stream);
+    const int rnd = tc_mode();
     TRY(launch_res_ln_bwd(M, D, d_out, sv->z, sv->mean, sv->rstd, w->ln_gamma, dropout_rate, dropout_key,
-                          d_x, accumulate_dx, sc->d_z, gw->ln_gamma, gw->ln_beta, s));
+                          d_x, accumulate_dx, sc->d_z, gw->ln_gamma, gw->ln_beta, rnd, s));
     // DenseLinear, then ReLU mask on the way into DenseRelu
-    TRY(linear_bwd(M, D, D, sv->h, w->w2, sc->d_z, gw->w2, gw->b2, sc->d_h, 0, sv->h, s));
-    TRY(linear_bwd(M, D, D, x, w->w1, sc->d_h, gw->w1, gw->b1, d_x, 1, nullptr, s));
+    TRY(linear_bwd(M, D, D, sv->h, w->w2, sc->d_z, gw->w2, gw->b2, sc->d_h, 0, sv->h, rnd, s));
+    TRY(linear_bwd(M, D, D, x, w->w1, sc->d_h, gw->w1, gw->b1, d_x, 1, nullptr, 0, s));
     return BDETR_OK;
 }
 
 API int bdetr_add_positional_fwd(int B, int L, int D, const float *x, const float *pos, float *out, void *stream)
 {
     BDETR_REQUIRE(x && pos && out, BDETR_E_NULL, "null pointer");
-    return launch_add_rows_fwd(B, L, D, x, pos, out, as_stream(stream));
+    return launch_add_rows_fwd(B, L, D, x, pos, out, tc_mode(), as_stream(stream));
 }
 API int bdetr_add_positional_bwd(int B, int L, int D, const float *d_out, float *d_pos, void *stream)
 {
@@ -116,11 +124,15 @@ API int bdetr_add_positional_bwd(int B, int L, int D, const float *d_out, float 
 API int bdetr_tile_queries_fwd(int B, int Q, int D, const float *q0, float *out, void *stream)
 {
     BDETR_REQUIRE(q0 && out, BDETR_E_NULL, "null pointer");
-    return launch_tile_rows(B, Q, D, q0, out, as_stream(stream));
+    return launch_tile_rows(B, Q, D, q0, out, tc_mode(), as_stream(stream));
 }
 API int bdetr_accumulate(size_t n, const float *x, float *y, void *stream)
 {
     return launch_accumulate(n, x, y, as_stream(stream));
+}
+API int bdetr_round_tf32(size_t n, const float *src, float *dst, void *stream)
+{
+    return launch_round_tf32(n, src, dst, as_stream(stream));
 }
 
 API int bdetr_head_fwd(int M, int D, int Dh, int Nout, int kind, int training, float mult,
@@ -128,12 +140,12 @@ API int bdetr_head_fwd(int M, int D, int Dh, int Nout, int kind, int training, f
                        float *cum, int cum_init, const bdetr_head_saved *sv, void *stream)
 {
     BDETR_REQUIRE(M > 0 && D > 0 && Dh > 0 && Nout > 0, BDETR_E_BAD_SHAPE, "bad shape");
-    BDETR_REQUIRE(x && w && cum && sv && sv->h && sv->hn && sv->bn_mean && sv->bn_rstd && sv->act, BDETR_E_NULL, "null pointer");
+    BDETR_REQUIRE(x && w && cum && sv && sv->h && sv->hn && sv->bn_mean && sv->bn_rstd && sv->bn_acc && sv->act, BDETR_E_NULL, "null pointer");
     cudaStream_t s = as_stream(stream);
-    TRY(linear_fwd(M, Dh, D, x, w->w1, w->b1, 1, sv->h, s));
+    TRY(linear_fwd(M, Dh, D, x, w->w1, w->b1, 1, sv->h, 0, s));
     TRY(launch_bn_fwd(M, Dh, sv->h, w->bn_gamma, w->bn_beta, w->bn_moving_mean, w->bn_moving_var, bn_eps, bn_momentum,
-                      training, sv->hn, sv->bn_mean, sv->bn_rstd, s));
-    TRY(linear_fwd(M, Nout, Dh, sv->hn, w->w2, w->b2, 0, sv->act, s));
+                      training, sv->bn_acc, sv->hn, sv->bn_mean, sv->bn_rstd, s));
+    TRY(linear_fwd(M, Nout, Dh, sv->hn, w->w2, w->b2, 0, sv->act, 0, s));
     TRY(launch_head_act_fwd(M, Nout, kind, mult, sv->act, cum, cum_init, s));
     return BDETR_OK;
 }
@@ -149,8 +161,9 @@ API int bdetr_head_bwd(int M, int D, int Dh, int Nout, int kind, float mult,
     BDETR_REQUIRE(x && w && sv && d_cum && d_x && gw && sc && sc->d_logits && sc->d_hn && sc->d_h, BDETR_E_NULL, "null pointer");
     cudaStream_t s = as_stream(stream);
     TRY(launch_head_act_bwd(M, Nout, kind, mult, sv->act, d_cum, sc->d_logits, s));
-    TRY(linear_bwd(M, Nout, Dh, sv->hn, w->w2, sc->d_logits, gw->w2, gw->b2, sc->d_hn, 0, nullptr, s));
-    TRY(launch_bn_relu_bwd(M, Dh, sv->h, sc->d_hn, w->bn_gamma, sv->bn_mean, sv->bn_rstd, sc->d_h, gw->bn_gamma, gw->bn_beta, s));
-    TRY(linear_bwd(M, Dh, D, x, w->w1, sc->d_h, gw->w1, gw->b1, d_x, accumulate_dx, nullptr, s));
+    TRY(linear_bwd(M, Nout, Dh, sv->hn, w->w2, sc->d_logits, gw->w2, gw->b2, sc->d_hn, 0, nullptr, 0, s));
+    TRY(launch_bn_relu_bwd(M, Dh, sv->h, sc->d_hn, w->bn_gamma, sv->bn_mean, sv->bn_rstd, sv->bn_acc, sc->d_h, gw->bn_gamma,
+                           gw->bn_beta, tc_mode(), s));
+    TRY(linear_bwd(M, Dh, D, x, w->w1, sc->d_h, gw->w1, gw->b1, d_x, accumulate_dx, nullptr, 0, s));
     return BDETR_OK;
 }

@@ -56,6 +56,7 @@ class Layer:
         self._weights: dict[str, torch.Tensor] = {}
         self._grads: dict[str, torch.Tensor] = {}
         self._non_trainable: set[str] = set()
+        self._shadow: dict[str, torch.Tensor] = {}     # tf32-rounded copies of the Dense kernels (tensor-core mode)
         self._struct_cache = None
         self.last_ctx = None
 
@@ -85,6 +86,13 @@ class Layer:
             yield base + k, self, k
         for sub in self.sublayers():
             yield from sub.named_weights(base)
+
+    def gemm_weights(self):
+        """Weights as the GEMMs should read them: tf32-rounded shadows of the Dense kernels in tensor-core mode."""
+        from . import _lib
+        if self._shadow and _lib.load().bdetr_get_mode() == _lib.MODE_TF32:
+            return {**self._weights, **self._shadow}, 1
+        return self._weights, 0
 
     def invalidate(self):
         self._struct_cache = None

@@ -46,15 +46,16 @@ class _Head(Layer):
         self.add_weight(f"{self.dense2}/bias", np.zeros(self.num_out, np.float32))
 
     def _structs(self):
-        if self._struct_cache is None:
+        w, mode = self.gemm_weights()
+        if self._struct_cache is None or self._struct_cache[2] != mode:
             def pack(s, stats):
                 return _struct(_lib.HeadParams, {
                     "w1": s[f"{self.dense1}/kernel"], "b1": s[f"{self.dense1}/bias"],
                     "bn_gamma": s["BatchNorm/gamma"], "bn_beta": s["BatchNorm/beta"],
                     "bn_moving_mean": stats.get("BatchNorm/moving_mean"), "bn_moving_var": stats.get("BatchNorm/moving_variance"),
                     "w2": s[f"{self.dense2}/kernel"], "b2": s[f"{self.dense2}/bias"]})
-            self._struct_cache = (pack(self._weights, self._weights), pack(self._grads, {}))
-        return self._struct_cache
+            self._struct_cache = (pack(w, self._weights), pack(self._grads, {}), mode)
+        return self._struct_cache[:2]
 
     def forward(self, inputs, training=False, cum=None, mult=1.0):
         """Returns (post-activation prediction of THIS head, ctx).  If `cum` is given the kernel also does
@@ -67,7 +68,7 @@ class _Head(Layer):
                              "Conv1D re-projection of the prediction axis is not on the supported path")
         M = x.shape[0] * x.shape[1]
         Dh, N = self.hidden_dim, self.num_out
-        sv = {"h": empty(M, Dh), "hn": empty(M, Dh), "bn_mean": empty(Dh), "bn_rstd": empty(Dh),
+        sv = {"h": empty(M, Dh), "hn": empty(M, Dh), "bn_mean": empty(Dh), "bn_rstd": empty(Dh), "bn_acc": empty(2 * Dh),
               "act": empty(x.shape[0], x.shape[1], N)}
         init = cum is None
         if init:

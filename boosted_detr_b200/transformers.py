@@ -71,8 +71,9 @@ class AttentionBlock(Layer):
         self.add_weight("LayerNorm/beta", np.zeros(D, np.float32))
 
     def _structs(self):
-        if self._struct_cache is None:
-            a = self.AttentionLayer
+        a = self.AttentionLayer
+        wa, mode = a.gemm_weights()
+        if self._struct_cache is None or self._struct_cache[2] != mode:
             def pack(src_a, src_s):
                 return _struct(_lib.AttnParams, {
                     "wq": src_a["QueryProjection/kernel"], "bq": src_a["QueryProjection/bias"],
@@ -80,8 +81,8 @@ class AttentionBlock(Layer):
                     "wv": src_a["ValueProjection/kernel"], "bv": src_a["ValueProjection/bias"],
                     "wo": src_a["OutputProjection/kernel"], "bo": src_a["OutputProjection/bias"],
                     "ln_gamma": src_s["LayerNorm/gamma"], "ln_beta": src_s["LayerNorm/beta"]})
-            self._struct_cache = (pack(a._weights, self._weights), pack(a._grads, self._grads))
-        return self._struct_cache
+            self._struct_cache = (pack(wa, self._weights), pack(a._grads, self._grads), mode)
+        return self._struct_cache[:2]
 
     def forward(self, inputs, training=False, dropout_key=0):
         query, key, value = (f32(t) for t in inputs)
@@ -149,12 +150,13 @@ class FeedForwardBlock(Layer):
         self.add_weight("LayerNorm/beta", np.zeros(D, np.float32))
 
     def _structs(self):
-        if self._struct_cache is None:
+        w, mode = self.gemm_weights()
+        if self._struct_cache is None or self._struct_cache[2] != mode:
             pack = lambda s: _struct(_lib.FfnParams, {"w1": s["DenseRelu/kernel"], "b1": s["DenseRelu/bias"],
                                                       "w2": s["DenseLinear/kernel"], "b2": s["DenseLinear/bias"],
                                                       "ln_gamma": s["LayerNorm/gamma"], "ln_beta": s["LayerNorm/beta"]})
-            self._struct_cache = (pack(self._weights), pack(self._grads))
-        return self._struct_cache
+            self._struct_cache = (pack(w), pack(self._grads), mode)
+        return self._struct_cache[:2]
 
     def forward(self, inputs, training=False, dropout_key=0):
         x = f32(inputs[0])

@@ -180,6 +180,9 @@ int bdetr_add_positional_bwd(int B, int L, int D, const float *d_out, float *d_p
 int bdetr_tile_queries_fwd(int B, int Q, int D, const float *q0, float *out, void *stream);
 /* y += x elementwise (gradient joins). */
 int bdetr_accumulate(size_t n, const float *x, float *y, void *stream);
+/* dst = round-to-nearest tf32(src) (may alias).  Tensor-core mode keeps tf32-rounded shadows of the Dense
+ * kernels and of the input features so that tcgen05's operand truncation is exact. */
+int bdetr_round_tf32(size_t n, const float *src, float *dst, void *stream);
 
 /* One prediction head = Dense(relu) -> BatchNorm -> Dense -> activation, post-activation output
  * added into the running (boosted) prediction:  cum += mult * act(...), mult = 2 for block 0
@@ -198,6 +201,7 @@ typedef struct {
     float *h;                /* [M,Dh] relu(x W1 + b1)               */
     float *hn;               /* [M,Dh] batch-normalised              */
     float *bn_mean, *bn_rstd;/* [Dh]                                 */
+    float *bn_acc;           /* [2*Dh] scratch for cross-CTA column sums */
     float *act;              /* [M,Nout] post-activation output      */
 } bdetr_head_saved;
 
