@@ -37,6 +37,19 @@ def shard_batch(inputs: dict, rank: int, world: int) -> dict:
     return out
 
 
+def allreduce_gradients(flat_grads: torch.Tensor):
+    """Sum of the per-replica gradients (each already scaled by 1/replicas): the only collective on the path."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+    return flat_grads
+
+
+def broadcast_tensor(t: torch.Tensor, src: int = 0):
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(t, src=src)
+    return t
+
+
 class DataParallel:
     """Attaches the gradient all-reduce to a BoostedDETR: model.train_step then computes
     sum over replicas of d(loss_replica / world)/d(theta)."""
@@ -50,13 +63,13 @@ class DataParallel:
         self.broadcast_weights()
 
     def allreduce(self, flat_grads: torch.Tensor):
-        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+        allreduce_gradients(flat_grads)
 
     def broadcast_weights(self):
         if self.world > 1:
             if self.model._flat is None:
                 self.model.build()
-            dist.broadcast(self.model._flat[0], src=0)
+            broadcast_tensor(self.model._flat[0])
             for _, o, k in self.model.named_weights():
                 if k in o._non_trainable:
-                    dist.broadcast(o._weights[k], src=0)
+                    broadcast_tensor(o._weights[k])

@@ -62,3 +62,50 @@ def lsap_c_solve(c):
     k = lsap_c().lsap_ref_f32(c.ctypes.data_as(ctypes.c_void_p), nr, nc, nc,
                               a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p))
     return k, a[:max(k, 0)], b[:max(k, 0)]
+
+
+def make_weights(rng, N, rows, cols, D, Q, C, A, perturb=True):
+    """All hot-path weights with the reference's Keras variable names, built on the
+    host with numpy only (usable by the oracle without a GPU)."""
+    def tn(shape, std):
+        x = rng.standard_normal(shape)
+        return (np.clip(x, -2, 2) * std).astype(np.float32)
+    w = {}
+    b = (lambda n: rng.normal(0, 0.1, n).astype(np.float32)) if perturb else (lambda n: np.zeros(n, np.float32))
+    g = (lambda n: (1 + rng.normal(0, 0.1, n)).astype(np.float32)) if perturb else (lambda n: np.ones(n, np.float32))
+
+    def attn(pfx):
+        for nm in ("QueryProjection", "KeyProjection", "ValueProjection", "OutputProjection"):
+            w[f"{pfx}/AttentionLayer/{nm}/kernel"] = tn((D, D), np.sqrt(1.0 / D))
+            w[f"{pfx}/AttentionLayer/{nm}/bias"] = b(D)
+        w[f"{pfx}/LayerNorm/gamma"], w[f"{pfx}/LayerNorm/beta"] = g(D), b(D)
+
+    def ffn(pfx):
+        for nm in ("DenseRelu", "DenseLinear"):
+            w[f"{pfx}/{nm}/kernel"] = tn((D, D), np.sqrt(1.0 / D))
+            w[f"{pfx}/{nm}/bias"] = b(D)
+        w[f"{pfx}/LayerNorm/gamma"], w[f"{pfx}/LayerNorm/beta"] = g(D), b(D)
+
+    def head(pfx, d1, d2, nout):
+        w[f"{pfx}/{d1}/kernel"], w[f"{pfx}/{d1}/bias"] = tn((D, D), np.sqrt(2.0 / D)), b(D)
+        w[f"{pfx}/BatchNorm/gamma"], w[f"{pfx}/BatchNorm/beta"] = g(D), b(D)
+        w[f"{pfx}/BatchNorm/moving_mean"] = b(D)
+        w[f"{pfx}/BatchNorm/moving_variance"] = rng.uniform(0.5, 1.5, D).astype(np.float32) if perturb else np.ones(D, np.float32)
+        w[f"{pfx}/{d2}/kernel"], w[f"{pfx}/{d2}/bias"] = tn((D, nout), np.sqrt(2.0 / (D + nout))), b(nout)
+
+    k = np.arange(rows * cols, dtype=np.float64)[:, None]
+    den = 2.0 * (1.0 + np.arange(D, dtype=np.float64))[None, :] / D
+    pos = np.where((k % 2) == 1, np.sin(k / den), np.cos(k / den)).reshape(rows, cols, D).astype(np.float32)
+    for i in range(N):
+        w[f"ImageEncoderAttention_{i}/positional_encoding"] = pos.copy()
+        attn(f"ImageEncoderAttention_{i}/EncoderBlock_0/SelfAttentionBlock")
+        ffn(f"ImageEncoderAttention_{i}/EncoderBlock_0/FeedForwardBlock")
+        if i >= 1:
+            attn(f"DecoderBlock_{i}/SelfAttentionBlock")
+        attn(f"DecoderBlock_{i}/JointAttentionBlock")
+        ffn(f"DecoderBlock_{i}/FeedForwardBlock")
+        head(f"CategoryPredictionHead_{i}", "DenseCateg", "DenseLogits", C)
+        head(f"AttributePredictionHead_{i}", "Dense", "DenseLinear", A)
+        head(f"BoxPredictionHead_{i}", "Dense", "BoxCoords", 4)
+    w["DecoderPrep/init_decoder_features"] = rng.normal(0, 0.5 if perturb else 0.02, (Q, D)).astype(np.float32)
+    return w
