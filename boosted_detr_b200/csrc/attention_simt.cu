@@ -222,6 +222,8 @@ int launch_attention_fwd(int B, int H, int Lq, int Lk, int d, const float *qp, c
 {
     BDETR_REQUIRE(d == HD, BDETR_E_UNSUPPORTED, "head dim must be 32 (D/H)");
     BDETR_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0, BDETR_E_BAD_SHAPE, "bad attention shape");
+    if (current_mode() == BDETR_MODE_TF32 && attention_umma_eligible(B, H, Lq, Lk, d, qp, kp, vp))
+        return launch_attention_fwd_umma(B, H, Lq, Lk, d, qp, kp, vp, o, lse, round_out, s);
     const float scale = 1.0f / sqrtf((float)d);
     dim3 grid(ceil_div(Lq, AT_THREADS), H, B);
     attention_fwd_kernel<<<grid, AT_THREADS, 0, s>>>(H, Lq, Lk, qp, kp, vp, o, lse, scale * LOG2E, round_out);

@@ -10,96 +10,13 @@
 //     wgrad     dW[K,N] += X[M,K]^T dY[M,N]    A MN-major, B MN-major   (split-K, fp32 red.add)
 // One CTA computes one 128 x BN output tile (x one K split): warp 0 = TMA producer, warp 1 = TMEM
 // allocator + single-thread MMA issuer, warps 2-5 = epilogue (one TMEM lane = one output row each).
-#include <cuda.h>
-#include "kernels.cuh"
+#include "umma.cuh"
 
 namespace bdetr {
 
 constexpr int UM_BM = 128;
 constexpr int UM_BK = 32;              // fp32 elements per stage along the contraction = one 128B swizzle row
 constexpr int UM_THREADS = 192;
-constexpr uint32_t SPIN_LIMIT = 1u << 28;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0, spins = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (!done && ++spins > SPIN_LIMIT) __trap();     // never hang the GPU: a protocol bug becomes an error
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32])
-{
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout the hardware
-// accepts for MN-major 32-bit operands: 128B rows, 4-row atoms, 32B chunks XOR-swizzled by row % 4).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)layout_type << 61;
-    return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b format TF32=2 [7,10)/[10,13),
-// a_major [15], b_major [16] (1 = MN-major), N>>3 [17,23), M>>4 [24,29).
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, int b_mn)
-{
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
 struct UmmaEpilogue {
     int M, N;
     const float *bias; int act; const float *relu_mask; int beta; int atomic_out; int round_out;
@@ -256,7 +173,8 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-static bool encode_map(CUtensorMap *map, const float *base, int rows, int cols, int ld, int box_cols, int box_rows, bool mn_major)
+bool encode_tensor_map_2d(CUtensorMap *map, const float *base, long long rows, int cols, int ld, int box_cols, int box_rows,
+                          bool mn_major)
 {
     EncodeTiledFn cuTensorMapEncodeTiled = encode_tiled_fn();
     if (!cuTensorMapEncodeTiled) return false;
@@ -307,10 +225,10 @@ int launch_gemm_umma(int M, int N, int K, const float *A, int lda, bool TA, cons
     const int BN = (N >= 128 && ceil_div(M, UM_BM) * ceil_div(N, 128) >= 120) ? 128 : 64;
     CUtensorMap ma, mb;
     bool ok;
-    if (!A_MN) ok = encode_map(&ma, A, M, K, lda, UM_BK, UM_BM, false);          // [M rows, K cols], box {32 k, 128 m}
-    else ok = encode_map(&ma, A, K, M, lda, 32, UM_BK, true);                   // [K rows, M cols], box {32 m, 32 k}
-    if (!B_MN) ok = ok && encode_map(&mb, B, N, K, ldb, UM_BK, BN, false);       // [N rows, K cols], box {32 k, BN n}
-    else ok = ok && encode_map(&mb, B, K, N, ldb, 32, UM_BK, true);             // [K rows, N cols], box {32 n, 32 k}
+    if (!A_MN) ok = encode_tensor_map_2d(&ma, A, M, K, lda, UM_BK, UM_BM, false);          // [M rows, K cols], box {32 k, 128 m}
+    else ok = encode_tensor_map_2d(&ma, A, K, M, lda, 32, UM_BK, true);                   // [K rows, M cols], box {32 m, 32 k}
+    if (!B_MN) ok = ok && encode_tensor_map_2d(&mb, B, N, K, ldb, UM_BK, BN, false);       // [N rows, K cols], box {32 k, BN n}
+    else ok = ok && encode_tensor_map_2d(&mb, B, K, N, ldb, 32, UM_BK, true);             // [K rows, N cols], box {32 n, 32 k}
     BDETR_REQUIRE(ok, BDETR_E_CUDA, "cuTensorMapEncodeTiled failed");
 
     UmmaEpilogue ep;

@@ -43,9 +43,10 @@ API int bdetr_attention_block_fwd(int B, int Lq, int Lk, int D, int H,
     cudaStream_t s = as_stream(stream);
     const int Mq = B * Lq, Mk = B * Lk;
     const int rnd = tc_mode();
-    TRY(linear_fwd(Mq, D, D, query, w->wq, w->bq, 0, sv->qp, 0, s));
-    TRY(linear_fwd(Mk, D, D, key, w->wk, w->bk, 0, sv->kp, 0, s));
-    TRY(linear_fwd(Mk, D, D, value, w->wv, w->bv, 0, sv->vp, 0, s));
+    // q/k/v feed the tcgen05 attention MMAs in tensor-core mode: store them tf32-rounded
+    TRY(linear_fwd(Mq, D, D, query, w->wq, w->bq, 0, sv->qp, rnd, s));
+    TRY(linear_fwd(Mk, D, D, key, w->wk, w->bk, 0, sv->kp, rnd, s));
+    TRY(linear_fwd(Mk, D, D, value, w->wv, w->bv, 0, sv->vp, rnd, s));
     TRY(launch_attention_fwd(B, H, Lq, Lk, D / H, sv->qp, sv->kp, sv->vp, sv->o, sv->lse, rnd, s));
     // sv->o is [B,H,Lq,d]; read back as [B*Lq, D] with no permute (reference transformers.py:100)
     TRY(linear_fwd(Mq, D, D, sv->o, w->wo, w->bo, 0, sv->z, 0, s));

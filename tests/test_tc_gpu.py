@@ -104,3 +104,54 @@ def test_model_train_step_tf32(tc_mode, attribute_weight):
             if not k.startswith("AttributePredictionHead"):      # no gradient reaches the attribute head
                 assert e < 2e-2, k
     assert flips == 0
+
+
+@pytest.mark.parametrize("B,Lq,Lk,selfattn", [(2, 400, 400, True), (2, 100, 400, False), (2, 100, 100, True),
+                                              (1, 1050, 1050, True), (3, 130, 257, False)])
+def test_attention_block_tf32(tc_mode, B, Lq, Lk, selfattn):
+    """tcgen05 flash attention (S = QKt and PV on the tensor cores, scores only in TMEM) inside AttentionBlock."""
+    from oracle import reference_path as R
+    from boosted_detr_b200.layers import Layer
+    from boosted_detr_b200.transformers import AttentionBlock
+    rng = np.random.default_rng(Lq * 7 + Lk)
+    Layer._rng = np.random.default_rng(1)
+    D, H = 256, 8
+    q = rng.standard_normal((B, Lq, D)).astype(np.float32)
+    k = q if selfattn else rng.standard_normal((B, Lk, D)).astype(np.float32)
+    v = rng.standard_normal((B, Lk, D)).astype(np.float32)
+    go = rng.standard_normal((B, Lq, D)).astype(np.float32)
+    blk = AttentionBlock(H, name="blk")
+    dq = torch.from_numpy(q).cuda()
+    dk = dq if selfattn else torch.from_numpy(k).cuda()
+    dv = torch.from_numpy(v).cuda()
+    out, ctx = blk.forward([dq, dk, dv], training=False)
+    for n, o, kk in blk.named_weights():
+        if kk.endswith("bias") or kk.endswith("beta"):
+            o._weights[kk].copy_(torch.from_numpy(rng.normal(0, 0.1, o._weights[kk].shape).astype(np.float32)))
+    out, ctx = blk.forward([dq, dk, dv], training=False)
+    d_q, d_k, d_v = blk.backward(ctx, torch.from_numpy(go).cuda())
+    torch.cuda.synchronize()
+    w = {n[len("blk/"):]: o._weights[kk].cpu().numpy() for n, o, kk in blk.named_weights()}
+    p = R.params_to_torch({"p/" + n: a for n, a in w.items()}, torch.float64, requires_grad=True)
+    tq = torch.tensor(q, dtype=torch.float64, requires_grad=True)
+    tk = tq if selfattn else torch.tensor(k, dtype=torch.float64, requires_grad=True)
+    tv = torch.tensor(v, dtype=torch.float64, requires_grad=True)
+    ref = R.attention_block(tq, tk, tv, p, "p", H, R.Dropout(None), 0, False)
+    (ref * torch.tensor(go, dtype=torch.float64)).sum().backward()
+    # raw attention output and log-sum-exp against a direct fp64 computation from the saved (rounded) q/k/v
+    sv = ctx["saved"]
+    qp, kp, vp = (sv[n].cpu().numpy().astype(np.float64) for n in ("qp", "kp", "vp"))
+    d = D // H
+    qh = qp.reshape(B, Lq, H, d).transpose(0, 2, 1, 3); kh = kp.reshape(B, Lk, H, d).transpose(0, 2, 1, 3)
+    vh = vp.reshape(B, Lk, H, d).transpose(0, 2, 1, 3)
+    s = qh @ kh.transpose(0, 1, 3, 2) / np.sqrt(d)
+    pm = np.exp(s - s.max(-1, keepdims=True)); pm /= pm.sum(-1, keepdims=True)
+    e_o = nerr(sv["o"].cpu().numpy(), pm @ vh)
+    lse_ref = (np.log(np.exp(s - s.max(-1, keepdims=True)).sum(-1)) + s.max(-1)) / np.log(2.0)
+    e_lse = nerr(sv["lse"].cpu().numpy(), lse_ref)
+    e = nerr(out.cpu().numpy(), ref.detach().numpy())
+    print(f"tf32 attention B{B} Lq{Lq} Lk{Lk}: o {e_o:.2e} lse {e_lse:.2e} block out {e:.2e} "
+          f"d_query {nerr(d_q.cpu().numpy(), tq.grad.numpy()):.2e} d_value {nerr(d_v.cpu().numpy(), tv.grad.numpy()):.2e}")
+    assert e_o < 1e-3 and e_lse < 1e-4
+    assert e < 2e-3
+    assert nerr(d_q.cpu().numpy(), tq.grad.numpy()) < 5e-3
