@@ -53,6 +53,7 @@ PROTOTYPES = {
     "bdetr_matched_loss_bwd": (c_int, [I, I, I, I, I, P, P, P, P, P, P, P, P, P, F, F, F, F, F, P, P, P, P]),
     "bdetr_attention_block_fwd": (c_int, [I, I, I, I, I, P, P, P, POINTER(AttnParams), F, c_uint32, F, P,
                                           POINTER(AttnSaved), P]),
+    "bdetr_attention_core_fwd": (c_int, [I, I, I, I, I, P, P, P, P, P, P]),
     "bdetr_attention_block_bwd": (c_int, [I, I, I, I, I, P, P, P, POINTER(AttnParams), F, c_uint32,
                                           POINTER(AttnSaved), P, P, P, P, I, POINTER(AttnParams),
                                           POINTER(AttnScratch), P]),

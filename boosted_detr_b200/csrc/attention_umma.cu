@@ -8,8 +8,9 @@
 //                   S[128x128]  = Q Kt        A, B K-major from shared memory (SWIZZLE_128B)      -> TMEM cols 0..127
 //                   Ot[128x32]  = P V         A = P from TMEM, B = V MN-major (SWIZZLE_128B_BASE32B) -> TMEM cols 128..159
 //   warps 2..5  softmax: one thread per query row (TMEM lane).  Two passes over the S row in TMEM (row max,
-//               then exp2 / row sum), P written back in place over S (tf32-rounded, so the MMA's operand
-//               truncation is exact), running (m, l, o[32]) in registers: o = o*alpha + Ot after each tile.
+//               then exp2 / row sum), P written back in place over S (masked to tf32 precision, and the row sum
+//               taken over the masked values, so the MMA's operand truncation is exact and cancels in the
+//               normalisation), running (m, l, o[32]) in registers: o = o*alpha + Ot after each tile.
 // Keeping O in registers makes the online-softmax rescale free (no TMEM correction pass); two CTAs per SM
 // (80 KB shared memory, 256 TMEM columns each) overlap one CTA's softmax with the other's MMAs.
 // Output layout [B,H,Lq,d] (quirk Q1), log-sum-exp in log2 units like the SIMT kernel (shared backward).
@@ -112,30 +113,45 @@ attention_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
             const int valid = min(FA_KT, Lk - t * FA_KT);
             mbar_wait(s_full, t & 1);
             tc_fence_after();
-            // pass 1: row maximum of the raw scores
+            // pass 1: row maximum of the raw scores (next chunk's TMEM load in flight while this one is reduced)
+            const bool full_tile = valid == FA_KT;            // only the last tile of a ragged Lk needs masking
+            uint32_t ra[32], rb[32];
             float mx = -CUDART_INF_F;
-#pragma unroll 1
-            for (int c0 = 0; c0 < FA_KT; c0 += 32) {
-                float v[32];
-                tmem_ld32(lane_addr + c0, v);
+            tmem_ld32_issue(lane_addr, ra);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c0 + i < valid) ? v[i] : -CUDART_INF_F);
+            for (int c = 0; c < FA_KT / 32; ++c) {
+                uint32_t *cur = (c & 1) ? rb : ra, *nxt = (c & 1) ? ra : rb;
+                tmem_ld32_wait(cur);
+                if (c + 1 < FA_KT / 32) tmem_ld32_issue(lane_addr + (c + 1) * 32, nxt);
+                if (full_tile) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < valid) ? __uint_as_float(cur[i]) : -CUDART_INF_F);
+                }
             }
             const float m_new = fmaxf(m, mx * scale_log2);
-            const float alpha = exp2f(m - m_new);                 // first tile: exp2(-inf) = 0
-            // pass 2: P = exp2(s*c - m_new), written back over S
+            const float alpha = ex2_approx(m - m_new);            // first tile: exp2(-inf) = 0
+            // pass 2: P = exp2(s*c - m_new) rounded to tf32, written back over S
             float psum = 0.0f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < FA_KT; c0 += 32) {
-                float v[32];
-                tmem_ld32(lane_addr + c0, v);
+            tmem_ld32_issue(lane_addr, ra);
+#pragma unroll
+            for (int c = 0; c < FA_KT / 32; ++c) {
+                uint32_t *cur = (c & 1) ? rb : ra, *nxt = (c & 1) ? ra : rb;
+                tmem_ld32_wait(cur);
+                if (c + 1 < FA_KT / 32) tmem_ld32_issue(lane_addr + (c + 1) * 32, nxt);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float p = (c0 + i < valid) ? tf32_rn(exp2f(fmaf(v[i], scale_log2, -m_new))) : 0.0f;
-                    v[i] = p;
-                    psum += p;
+                    // keep the 10 mantissa bits the tf32 MMA will read (one LOP on the ALU pipe; cvt.rna would
+                    // compete with ex2 for the XU pipe) and sum exactly those weights, so numerator and
+                    // denominator of the softmax use identical values and the truncation bias cancels.
+                    uint32_t pb = __float_as_uint(ex2_approx(fmaf(__uint_as_float(cur[i]), scale_log2, -m_new))) & 0xFFFFE000u;
+                    if (!full_tile && c * 32 + i >= valid) pb = 0u;
+                    cur[i] = pb;
+                    psum += __uint_as_float(pb);
                 }
-                tmem_st32(lane_addr + c0, v);
+                tmem_st32_u(lane_addr + c * 32, cur);
             }
             tmem_st_wait();
             tc_fence_before();

@@ -54,6 +54,13 @@ API int bdetr_attention_block_fwd(int B, int Lq, int Lk, int D, int H,
     return BDETR_OK;
 }
 
+API int bdetr_attention_core_fwd(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
+                                 float *o, float *lse, void *stream)
+{
+    BDETR_REQUIRE(qp && kp && vp && o && lse, BDETR_E_NULL, "null pointer");
+    return launch_attention_fwd(B, H, Lq, Lk, d, qp, kp, vp, o, lse, 0, as_stream(stream));
+}
+
 API int bdetr_attention_block_bwd(int B, int Lq, int Lk, int D, int H,
                                   const float *query, const float *key, const float *value,
                                   const bdetr_attn_params *w, float dropout_rate, uint32_t dropout_key,

@@ -135,6 +135,12 @@ int bdetr_attention_block_fwd(int B, int Lq, int Lk, int D, int H,
                               const bdetr_attn_params *w, float dropout_rate, uint32_t dropout_key,
                               float ln_eps, float *out, const bdetr_attn_saved *saved, void *stream);
 
+/* The attention core alone (transformers.py:77-97): qp [B,Lq,H*d], kp/vp [B,Lk,H*d] are the projected tensors
+ * (head = d-column slice), o [B,H,Lq,d], lse [B,H,Lq] (log2 units).  Scores are never written to HBM.
+ * Tensor-core mode runs the tcgen05/TMEM flash kernel; fp32 mode the SIMT kernel. */
+int bdetr_attention_core_fwd(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
+                             float *o, float *lse, void *stream);
+
 /* Backward of the above.  Parameter gradients are ACCUMULATED into *gw.  d_query/d_key/d_value
  * may be NULL (not needed); acc_flags bit0/1/2 = accumulate into d_query/d_key/d_value instead of
  * overwriting. */

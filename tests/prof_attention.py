@@ -1,0 +1,12 @@
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from boosted_detr_b200 import _lib
+from boosted_detr_b200.device import ptr, stream_ptr
+lib = _lib.load(); lib.bdetr_set_mode(_lib.MODE_TF32)
+B, Lq, Lk, H, d = 4, 4096, 4096, 8, 32
+D = H * d
+q = torch.randn(B, Lq, D, device="cuda"); k = torch.randn(B, Lk, D, device="cuda"); v = torch.randn(B, Lk, D, device="cuda")
+o = torch.empty(B, H, Lq, d, device="cuda"); lse = torch.empty(B, H, Lq, device="cuda")
+for _ in range(3):
+    _lib.call("bdetr_attention_core_fwd", B, H, Lq, Lk, d, ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), stream_ptr())
+torch.cuda.synchronize(); print("ok")
