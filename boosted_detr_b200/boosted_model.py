@@ -187,12 +187,22 @@ class BoostedDETR:
         k = lambda s: dropout_key(self.dropout_seed, 8 * i + s)
         return {"enc": [(k(SITE_ENC_ATTN), k(SITE_ENC_FFN))], "dec": (k(SITE_DEC_SELF), k(SITE_DEC_CROSS), k(SITE_DEC_FFN))}
 
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream()
+        return self._side
+
     # -- forward -------------------------------------------------------------------------------
     def forward(self, feats, y_true, training):
         """The hot loop (reference :199-246).  Returns (y_pred, ctx)."""
         N = self.num_decoder_blocks
         use_dropout = training and self.dropout_seed is not None
         x = feats
+        # The matcher of block i (cost matrix -> per-image assignment -> matched loss) does not feed block i+1's
+        # forward and is latency-bound on a handful of warps, so it runs on a side stream underneath the next
+        # block's GEMMs / attention and is joined before the backward (also captured as a parallel graph branch).
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if training else None
         if self.tensor_core_mode():
             self.refresh_shadow()
             x = torch.empty_like(feats)                        # the block input feeds tcgen05 GEMMs: round it too
@@ -223,7 +233,11 @@ class BoostedDETR:
             cums = new_cums
             blocks.append({"enc": c_enc, "prep": c_prep, "dec": c_dec, "heads": c_heads})
             if training:
-                loss_ctxs.append(self.loss_fn.forward(y_true, cums))
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    loss_ctxs.append(self.loss_fn.forward(y_true, cums))
+        if training:
+            main.wait_stream(side)
         return cums, {"blocks": blocks, "loss": loss_ctxs, "y_true": y_true}
 
     def backward(self, ctx, gscale=1.0):

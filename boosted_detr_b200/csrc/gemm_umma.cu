@@ -129,17 +129,32 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int n = n0 + c0 + lane;
             if (n < ep.N) {
                 const float bias_n = (ep.bias && (!ep.atomic_out || blockIdx.z == 0)) ? ep.bias[n] : 0.0f;
-                for (int r = 0; r < nrows; ++r) {
-                    const size_t off = (size_t)(m0 + q * 32 + r) * ep.ldc + n;
-                    float x = stage[q][r][lane] + bias_n;
-                    if (ep.atomic_out) {
-                        atomicAdd(ep.C + off, x);
-                    } else {
-                        if (ep.beta) x += ep.C[off];
-                        if (ep.act == 1) x = fmaxf(x, 0.0f);
-                        if (ep.relu_mask && !(ep.relu_mask[off] > 0.0f)) x = 0.0f;
-                        if (ep.round_out) x = tf32_rn(x);
-                        ep.C[off] = x;
+                float *cbase = ep.C + (size_t)(m0 + q * 32) * ep.ldc + n;
+                if (ep.atomic_out) {
+                    for (int r = 0; r < nrows; ++r) atomicAdd(cbase + (size_t)r * ep.ldc, stage[q][r][lane] + bias_n);
+                } else {
+                    // all global reads of the chunk are issued before the first store (the row loop would otherwise
+                    // serialise one L2 round trip per row behind the store it may alias)
+                    float cold[32], mk[32];
+                    if (ep.beta) {
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) cold[r] = r < nrows ? cbase[(size_t)r * ep.ldc] : 0.0f;
+                    }
+                    if (ep.relu_mask) {
+                        const float *mbase = ep.relu_mask + (size_t)(m0 + q * 32) * ep.ldc + n;
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) mk[r] = r < nrows ? mbase[(size_t)r * ep.ldc] : 0.0f;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        if (r < nrows) {
+                            float x = stage[q][r][lane] + bias_n;
+                            if (ep.beta) x += cold[r];
+                            if (ep.act == 1) x = fmaxf(x, 0.0f);
+                            if (ep.relu_mask && !(mk[r] > 0.0f)) x = 0.0f;
+                            if (ep.round_out) x = tf32_rn(x);
+                            cbase[(size_t)r * ep.ldc] = x;
+                        }
                     }
                 }
             }
