@@ -236,6 +236,8 @@ int launch_attention_bwd(int B, int H, int Lq, int Lk, int d, const float *qp, c
                          float *d_qp, float *d_kp, float *d_vp, int round_out, cudaStream_t s)
 {
     BDETR_REQUIRE(d == HD, BDETR_E_UNSUPPORTED, "head dim must be 32 (D/H)");
+    if (current_mode() == BDETR_MODE_TF32 && attention_bwd_umma_eligible(B, H, Lq, Lk, d, qp, kp, vp, d_o))
+        return launch_attention_bwd_umma(B, H, Lq, Lk, d, qp, kp, vp, o, lse, d_o, delta, d_qp, d_kp, d_vp, round_out, s);
     const float scale = 1.0f / sqrtf((float)d);
     dim3 gq(ceil_div(Lq, AT_THREADS), H, B);
     attention_bwd_dq_kernel<<<gq, AT_THREADS, 0, s>>>(H, Lq, Lk, qp, kp, vp, o, lse, d_o, delta, d_qp, scale, scale * LOG2E, round_out);

@@ -34,6 +34,12 @@ bool attention_umma_eligible(int B, int H, int Lq, int Lk, int d, const float *q
 int launch_attention_fwd_umma(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
                               float *o, float *lse, int round_out, cudaStream_t s);
 
+bool attention_bwd_umma_eligible(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
+                                 const float *d_o);
+int launch_attention_bwd_umma(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
+                              const float *o, const float *lse, const float *d_o, float *delta,
+                              float *d_qp, float *d_kp, float *d_vp, int round_out, cudaStream_t s);
+
 // z = resid + dropout(z) (in place), out = LN(z); saves mean/rstd.
 int launch_res_ln_fwd(int M, int D, const float *resid, float *z, const float *gamma, const float *beta, float eps,
                       float rate, uint32_t key, float *out, float *mean, float *rstd, int round_out, cudaStream_t s);

@@ -78,7 +78,8 @@ API int bdetr_attention_block_bwd(int B, int Lq, int Lk, int D, int H,
     TRY(launch_res_ln_bwd(Mq, D, d_out, sv->z, sv->mean, sv->rstd, w->ln_gamma, dropout_rate, dropout_key,
                           d_query, acc_flags & 1, sc->d_z, gw->ln_gamma, gw->ln_beta, rnd, s));
     // output projection
-    TRY(linear_bwd(Mq, D, D, sv->o, w->wo, sc->d_z, gw->wo, gw->bo, sc->d_o, 0, nullptr, 0, s));
+    // d_o feeds the tcgen05 attention backward MMAs in tensor-core mode: store it tf32-rounded
+    TRY(linear_bwd(Mq, D, D, sv->o, w->wo, sc->d_z, gw->wo, gw->bo, sc->d_o, 0, nullptr, rnd, s));
     TRY(launch_attention_bwd(B, H, Lq, Lk, D / H, sv->qp, sv->kp, sv->vp, sv->o, sv->lse, sc->d_o, sc->delta,
                              sc->d_qp, sc->d_kp, sc->d_vp, rnd, s));
     TRY(linear_bwd(Mq, D, D, query, w->wq, sc->d_qp, gw->wq, gw->bq, d_query, 1, nullptr, 0, s));

@@ -155,3 +155,12 @@ def test_attention_block_tf32(tc_mode, B, Lq, Lk, selfattn):
     assert e_o < 1e-3 and e_lse < 1e-4
     assert e < 2e-3
     assert nerr(d_q.cpu().numpy(), tq.grad.numpy()) < 5e-3
+    assert nerr(d_v.cpu().numpy(), tv.grad.numpy()) < 1e-2
+    if not selfattn:
+        e_k = nerr(d_k.cpu().numpy(), tk.grad.numpy())
+        print(f"   d_key {e_k:.2e}")
+        assert e_k < 1e-2
+    werr = {n: nerr(o._grads[kk].cpu().numpy(), p["p/" + n[len("blk/"):]].grad.numpy()) for n, o, kk in blk.named_weights()
+            if "KeyProjection/bias" not in n}
+    print("   weight grads worst:", max(werr.items(), key=lambda kv: kv[1]))
+    assert max(werr.values()) < 1e-2
