@@ -127,6 +127,7 @@ int launch_gemm(int M, int N, int K, const float *A, int lda, bool TA, const flo
     BDETR_REQUIRE(A && B && C, BDETR_E_NULL, "null operand");
     if (current_mode() == BDETR_MODE_TF32 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
         (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
+        !(beta && (act || relu_mask || round_out)) &&      // accumulate goes through TMA reduce-add: plain sums only
         umma_gemm_eligible(M, N, K, A, lda, TA, B, ldb, TB, ldc))
         return launch_gemm_umma(M, N, K, A, lda, TA, B, ldb, TB, bias, act, relu_mask, beta, round_out, C, ldc, s);
     GemmArgs g;

@@ -22,11 +22,13 @@ struct UmmaEpilogue {
     const float *bias; int act; const float *relu_mask; int beta; int atomic_out; int round_out;
     float *C; int ldc;
     int num_kb, kb_per_split;
+    long long *dbg;       // optional clock64 timeline of CTA (0,0,0) (bdetr_debug_set_timeline)
 };
 
 template <int BN, int UM_STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(UM_THREADS, 1)
-gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, UmmaEpilogue ep)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_c, UmmaEpilogue ep)
 {
     constexpr uint32_t A_STAGE = UM_BM * UM_BK * 4;      // 16 KB
     constexpr uint32_t B_STAGE = BN * UM_BK * 4;
@@ -38,9 +40,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t *empty = full + UM_STAGES;
     uint64_t *accum_full = empty + UM_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
-    float (*stage)[32][33] = reinterpret_cast<float (*)[32][33]>(tmem_slot + 4);     // per-epilogue-warp transpose buffer
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool dbg_on = ep.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define UMMA_STAMP(slot) do { if (dbg_on) ep.dbg[slot] = clock64(); } while (0)
+    if (threadIdx.x == 0) UMMA_STAMP(0);
     const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
     const int kb_beg = blockIdx.z * ep.kb_per_split;
     const int kb_end = min(ep.num_kb, kb_beg + ep.kb_per_split);
@@ -59,11 +63,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) UMMA_STAMP(1);
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             for (int i = 0; i < nkb; ++i) {
+                if (i == 1) UMMA_STAMP(2);
                 const int s = i % UM_STAGES;
                 if (i >= UM_STAGES) mbar_wait(&empty[s], ((i / UM_STAGES) - 1) & 1);
                 mbar_expect_tx(&full[s], A_STAGE + B_STAGE);
@@ -90,6 +96,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % UM_STAGES;
                 mbar_wait(&full[s], (i / UM_STAGES) & 1);
+                if (i == 0) UMMA_STAMP(3);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_base = smem_u32(smem_a + s * A_STAGE), b_base = smem_u32(smem_b + s * B_STAGE);
 #pragma unroll
@@ -104,65 +111,85 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
             }
             umma_commit(accum_full);               // accumulator complete
+            UMMA_STAMP(4);
         }
     } else {
-        // ===== epilogue: warp w owns TMEM lanes 32*(w%4)..; each 32x32 block is transposed through shared
-        // memory so that global stores / reductions are 128-byte coalesced rows =====
+        // ===== epilogue: warp w owns TMEM lanes 32*(w%4)..  Each lane holds one output row; a 32x32 block goes to
+        // shared memory in the 128B-swizzled box layout (conflict-free 16-byte stores) and leaves through one TMA
+        // store -- or TMA reduce-add for accumulate / split-K -- which also clips the M and N tails.  The pipeline
+        // stages are free once the accumulator is complete, so the staging boxes reuse them. =====
         const int q = warp & 3;
         if (nkb > 0) {
             mbar_wait(accum_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        const int rows_left = ep.M - (m0 + q * 32);
-        const int nrows = rows_left < 32 ? (rows_left < 0 ? 0 : rows_left) : 32;
+        if (warp == 2 && lane == 0) UMMA_STAMP(5);
+        const int row = m0 + q * 32 + lane;
+        const bool add_bias = ep.bias && (!ep.atomic_out || blockIdx.z == 0);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c = 0; c < BN / 32; ++c) {
+            const int c0 = c * 32;
             float v[32];
             if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
             else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.0f;
             }
+            const int ncol = ep.N - (n0 + c0);                 // columns of this chunk inside the matrix
+            if (ncol > 0) {
+                if (add_bias) {
+                    if (ncol >= 32) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) stage[q][lane][i] = v[i];
-            __syncwarp();
-            const int n = n0 + c0 + lane;
-            if (n < ep.N) {
-                const float bias_n = (ep.bias && (!ep.atomic_out || blockIdx.z == 0)) ? ep.bias[n] : 0.0f;
-                float *cbase = ep.C + (size_t)(m0 + q * 32) * ep.ldc + n;
-                if (ep.atomic_out) {
-                    for (int r = 0; r < nrows; ++r) atomicAdd(cbase + (size_t)r * ep.ldc, stage[q][r][lane] + bias_n);
-                } else {
-                    // all global reads of the chunk are issued before the first store (the row loop would otherwise
-                    // serialise one L2 round trip per row behind the store it may alias)
-                    float cold[32], mk[32];
-                    if (ep.beta) {
-#pragma unroll
-                        for (int r = 0; r < 32; ++r) cold[r] = r < nrows ? cbase[(size_t)r * ep.ldc] : 0.0f;
-                    }
-                    if (ep.relu_mask) {
-                        const float *mbase = ep.relu_mask + (size_t)(m0 + q * 32) * ep.ldc + n;
-#pragma unroll
-                        for (int r = 0; r < 32; ++r) mk[r] = r < nrows ? mbase[(size_t)r * ep.ldc] : 0.0f;
-                    }
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                        if (r < nrows) {
-                            float x = stage[q][r][lane] + bias_n;
-                            if (ep.beta) x += cold[r];
-                            if (ep.act == 1) x = fmaxf(x, 0.0f);
-                            if (ep.relu_mask && !(mk[r] > 0.0f)) x = 0.0f;
-                            if (ep.round_out) x = tf32_rn(x);
-                            cbase[(size_t)r * ep.ldc] = x;
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4 *>(ep.bias + n0 + c0 + i);
+                            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
                         }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (i < ncol) v[i] += ep.bias[n0 + c0 + i];
                     }
                 }
+                if (ep.act == 1) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+                }
+                if (ep.relu_mask && row < ep.M) {
+                    const float *mrow = ep.relu_mask + (size_t)row * ep.ldc + n0 + c0;
+                    if (ncol >= 32) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 k4 = *reinterpret_cast<const float4 *>(mrow + i);
+                            if (!(k4.x > 0.f)) v[i] = 0.f; if (!(k4.y > 0.f)) v[i + 1] = 0.f;
+                            if (!(k4.z > 0.f)) v[i + 2] = 0.f; if (!(k4.w > 0.f)) v[i + 3] = 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (i < ncol && !(mrow[i] > 0.f)) v[i] = 0.f;
+                    }
+                }
+                if (ep.round_out) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = tf32_rn(v[i]);
+                }
+                uint8_t *box = smem + (size_t)(c * 4 + q) * 4096;      // [32 rows][128 B], swizzle = chunk ^ (row & 7)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4 *>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && m0 + q * 32 < ep.M) {
+                    if (ep.atomic_out || ep.beta) tma_reduce_add_2d(&map_c, box, n0 + c0, m0 + q * 32);
+                    else tma_store_2d(&map_c, box, n0 + c0, m0 + q * 32);
+                    tma_store_commit();
+                }
             }
-            __syncwarp();
         }
+        if (lane == 0) tma_store_wait_all();
     }
+    if (warp == 2 && lane == 0) UMMA_STAMP(6);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) UMMA_STAMP(7);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
     }
@@ -171,6 +198,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+long long *g_umma_timeline = nullptr;
 // cuTensorMapEncodeTiled is fetched through the runtime so that libbdetr.so has no link-time dependency on
 // libcuda.so.1 (the library must also load on GPU-less build hosts).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -204,7 +232,7 @@ bool encode_tensor_map_2d(CUtensorMap *map, const float *base, long long rows, i
 }
 
 template <int BN, int STAGES>
-static size_t umma_smem_bytes() { return (size_t)STAGES * (UM_BM * UM_BK * 4 + BN * UM_BK * 4) + (2 * STAGES + 1) * 8 + 16 + 4 * 32 * 33 * 4 + 1024; }
+static size_t umma_smem_bytes() { return (size_t)STAGES * (UM_BM * UM_BK * 4 + BN * UM_BK * 4) + (2 * STAGES + 1) * 8 + 64 + 1024; }
 
 bool umma_gemm_eligible(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB, int ldc)
 {
@@ -214,16 +242,19 @@ bool umma_gemm_eligible(int M, int N, int K, const float *A, int lda, bool TA, c
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_umma_inst(dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const UmmaEpilogue &ep, cudaStream_t s)
+static int launch_umma_inst(dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mc, const UmmaEpilogue &ep,
+                            cudaStream_t s)
 {
-    constexpr int STAGES = BN == 64 ? 3 : 4;        // BN=64: 89 KB per CTA -> two CTAs per SM overlap load and epilogue
+    // The grids of this workload are at most one wave, so a CTA's latency is the kernel's latency: keep the whole
+    // K = 256 extent (8 k-blocks) in flight -- TMA round trips are ~1000 cycles.  192 KB of stages either way.
+    constexpr int STAGES = BN == 64 ? 8 : 6;
     static bool optin = false;
     const size_t smem = umma_smem_bytes<BN, STAGES>();
     if (!optin) {
         BDETR_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<BN, STAGES, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         optin = true;
     }
-    gemm_umma_kernel<BN, STAGES, A_MN, B_MN><<<grid, UM_THREADS, smem, s>>>(ma, mb, ep);
+    gemm_umma_kernel<BN, STAGES, A_MN, B_MN><<<grid, UM_THREADS, smem, s>>>(ma, mb, mc, ep);
     BDETR_CHECK_LAUNCH("gemm_umma_kernel");
     return BDETR_OK;
 }
@@ -236,22 +267,25 @@ int launch_gemm_umma(int M, int N, int K, const float *A, int lda, bool TA, cons
     // operand majors: A K-major when stored [M,K]; MN-major when stored [K,M].  B K-major when stored [N,K];
     // MN-major when stored [K,N] (Keras kernels and dY).
     const bool A_MN = TA, B_MN = !TB;
-    // 128x128 tiles unless they would leave most SMs idle; 128x64 tiles run two CTAs per SM
-    const int BN = (N >= 128 && ceil_div(M, UM_BM) * ceil_div(N, 128) >= 120) ? 128 : 64;
+    // one CTA per SM (192 KB of pipeline stages): 128x64 tiles while they fit in one wave, else 128x128
+    const int BN = (N >= 128 && ceil_div(M, UM_BM) * ceil_div(N, 64) > 148) ? 128 : 64;
     CUtensorMap ma, mb;
     bool ok;
     if (!A_MN) ok = encode_tensor_map_2d(&ma, A, M, K, lda, UM_BK, UM_BM, false);          // [M rows, K cols], box {32 k, 128 m}
     else ok = encode_tensor_map_2d(&ma, A, K, M, lda, 32, UM_BK, true);                   // [K rows, M cols], box {32 m, 32 k}
     if (!B_MN) ok = ok && encode_tensor_map_2d(&mb, B, N, K, ldb, UM_BK, BN, false);       // [N rows, K cols], box {32 k, BN n}
     else ok = ok && encode_tensor_map_2d(&mb, B, K, N, ldb, 32, UM_BK, true);             // [K rows, N cols], box {32 n, 32 k}
+    CUtensorMap mc;
+    ok = ok && encode_tensor_map_2d(&mc, C, M, N, ldc, 32, 32, false);        // output boxes: 32 rows x 32 cols per epilogue warp
     BDETR_REQUIRE(ok, BDETR_E_CUDA, "cuTensorMapEncodeTiled failed");
 
     UmmaEpilogue ep;
+    ep.dbg = g_umma_timeline;
     ep.M = M; ep.N = N; ep.bias = bias; ep.act = act; ep.relu_mask = relu_mask; ep.beta = beta; ep.round_out = round_out; ep.C = C; ep.ldc = ldc;
     ep.num_kb = ceil_div(K, UM_BK);
     const int tiles = ceil_div(M, UM_BM) * ceil_div(N, BN);
     int splits = 1;
-    if (act == 0 && relu_mask == nullptr && !round_out && tiles < 74 && ep.num_kb >= 16) splits = min(ep.num_kb / 4, max(1, 296 / tiles));
+    if (act == 0 && relu_mask == nullptr && !round_out && tiles < 74 && ep.num_kb >= 16) splits = min(ep.num_kb / 4, max(1, 148 / tiles));
     ep.kb_per_split = ceil_div(ep.num_kb, splits);
     splits = ceil_div(ep.num_kb, ep.kb_per_split);
     ep.atomic_out = splits > 1;
@@ -259,10 +293,10 @@ int launch_gemm_umma(int M, int N, int K, const float *A, int lda, bool TA, cons
     dim3 grid(ceil_div(N, BN), ceil_div(M, UM_BM), splits);
 #define UMMA_DISPATCH(BN_)                                                                            \
     do {                                                                                              \
-        if (!A_MN && B_MN) return launch_umma_inst<BN_, false, true>(grid, ma, mb, ep, s);            \
-        if (!A_MN && !B_MN) return launch_umma_inst<BN_, false, false>(grid, ma, mb, ep, s);          \
-        if (A_MN && B_MN) return launch_umma_inst<BN_, true, true>(grid, ma, mb, ep, s);              \
-        return launch_umma_inst<BN_, true, false>(grid, ma, mb, ep, s);                               \
+        if (!A_MN && B_MN) return launch_umma_inst<BN_, false, true>(grid, ma, mb, mc, ep, s);            \
+        if (!A_MN && !B_MN) return launch_umma_inst<BN_, false, false>(grid, ma, mb, mc, ep, s);          \
+        if (A_MN && B_MN) return launch_umma_inst<BN_, true, true>(grid, ma, mb, mc, ep, s);              \
+        return launch_umma_inst<BN_, true, false>(grid, ma, mb, mc, ep, s);                               \
     } while (0)
     if (BN == 128) UMMA_DISPATCH(128);
     UMMA_DISPATCH(64);

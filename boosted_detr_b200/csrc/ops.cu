@@ -139,6 +139,12 @@ API int bdetr_accumulate(size_t n, const float *x, float *y, void *stream)
 {
     return launch_accumulate(n, x, y, as_stream(stream));
 }
+namespace bdetr { extern long long *g_umma_timeline; }
+API int bdetr_debug_set_timeline(long long *device_buf8)
+{
+    bdetr::g_umma_timeline = device_buf8;
+    return BDETR_OK;
+}
 API int bdetr_round_tf32(size_t n, const float *src, float *dst, void *stream)
 {
     return launch_round_tf32(n, src, dst, as_stream(stream));

@@ -227,6 +227,11 @@ int bdetr_head_bwd(int M, int D, int Dh, int Nout, int kind, float mult,
                    float *d_x, int accumulate_dx,
                    const bdetr_head_params *gw, const bdetr_head_scratch *scratch, void *stream);
 
+/* Debug aid: when non-NULL, CTA (0,0,0) of every tcgen05 GEMM writes eight clock64 stamps into this device
+ * buffer (entry, setup done, 2nd TMA issue, first stage landed, last MMA committed, accumulator ready,
+ * epilogue done, teardown).  Pass NULL to switch it off. */
+int bdetr_debug_set_timeline(long long *device_buf8);
+
 /* Generic row-major GEMM used by the entry points above, exported for tests and benchmarks:
  * C[M,N] = (beta ? C : 0) + op(A)[M,K] @ op(B)[K,N] (+ bias[N]) (relu if act==1).
  * transA: A is stored [K,M]; transB: B is stored [N,K]. */

