@@ -301,6 +301,7 @@ def main():
         # count by running one eager (non-graph) step
         dev_batch = {k: torch.from_numpy(v).cuda() for k, v in batch.items()}
         lib.bdetr_reset_launch_count()
+        model.grad_allreduce = None            # rank 0 only from here on: no collectives
         model.train_step(dev_batch, return_host=False)
         torch.cuda.synchronize()
         launches_per_step = lib.bdetr_launch_count()
