@@ -94,54 +94,72 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def time_kernel(fn, iters=30, warm=5, flush=None):
+def time_kernel(fn, reps=50, iters=7, flush=None):
+    """Average device time of one launch: `reps` back-to-back launches captured in a CUDA graph (no host launch
+    gaps; a single launch bracketed by events is floored at ~10 us by the event/launch overhead), median of
+    `iters` replays, CUDA events on the launching stream, L2 flushed before each replay."""
     import torch
-    for _ in range(warm):
+    for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
     ts = []
     for _ in range(iters):
         if flush is not None:
             flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record()
+        a.record(); g.replay(); b.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    return float(np.mean(ts)) * 1e-3        # seconds
+        ts.append(a.elapsed_time(b) / reps)
+    return float(np.median(ts)) * 1e-3        # seconds
 
 
 def roofline_block(cfg, B, flush, peaks):
-    """Dominant kernel of the step timed alone, live, with CUDA events on the launching stream."""
+    """Dominant kernel of the step (the Dense GEMM: ~330 of the ~820 launches and the largest share of device
+    time in profiles/), timed alone, live; the attention core and the cost-matrix kernel are reported beside it."""
     import torch
     from boosted_detr_b200 import _lib
     from boosted_detr_b200.device import ptr, stream_ptr
     L, D, H = cfg["rows"] * cfg["cols"], cfg["D"], cfg["H"]
     mode = _lib.load().bdetr_get_mode()
-    # encoder self-attention backward (dK/dV + dQ) is the largest single consumer in fp32 mode; in both
-    # modes the attention core is the kernel family the tensor-pipe target is stated for.
+    M = B * L
+    x = torch.randn(M, D, device="cuda"); wt = torch.randn(D, D, device="cuda"); bias = torch.randn(D, device="cuda")
+    y = torch.empty(M, D, device="cuda")
+    t_gemm = time_kernel(lambda: _lib.call("bdetr_gemm", M, D, D, ptr(x), 0, ptr(wt), 0, ptr(bias), 0, 0, ptr(y), stream_ptr()), flush=flush)
+    flops_gemm = 2.0 * M * D * D
     q, k, v = (torch.randn(B, L, D, device="cuda") for _ in range(3))
     o, lse = torch.empty(B, H, L, D // H, device="cuda"), torch.empty(B, H, L, device="cuda")
-    from boosted_detr_b200.transformers import AttentionBlock
-    blk = AttentionBlock(H, name="roofline_probe")
-    out, ctx = blk.forward([q, k, v], training=False)
-    lib = _lib.load()
-    sv = ctx["saved_struct"]
-    import ctypes
-    w, _ = blk._structs()
-    t_fwd_block = time_kernel(lambda: _lib.call("bdetr_attention_block_fwd", B, L, L, D, H, ptr(q), ptr(k), ptr(v), ctypes.byref(w),
-                                                0.0, 0, 1e-3, ptr(out), ctypes.byref(sv), stream_ptr()), flush=flush)
-    # GEMM alone: [B*L, D] x [D, D]
-    x = torch.randn(B * L, D, device="cuda"); wt = torch.randn(D, D, device="cuda"); y = torch.empty(B * L, D, device="cuda")
-    t_gemm = time_kernel(lambda: _lib.call("bdetr_gemm", B * L, D, D, ptr(x), 0, ptr(wt), 0, None, 0, 0, ptr(y), stream_ptr()), flush=flush)
-    flops_gemm = 2.0 * B * L * D * D
+    t_attn = time_kernel(lambda: _lib.call("bdetr_attention_core_fwd", B, H, L, L, D // H, ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), stream_ptr()), flush=flush)
     flops_attn = 4.0 * B * L * L * D
-    t_attn = max(t_fwd_block - 4 * t_gemm, 1e-9)      # block = 4 projections + attention core + LN
-    peak = peaks.get("bf16_tflops", 1590.0)
-    ach = flops_attn / t_attn / 1e12
-    return {"bound": "tensor", "kernel": "attention_fwd (encoder self-attention core, L=%d)" % L,
-            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if "bf16_tflops" in peaks else "fallback 1590",
-            "gemm_MxNxK": [B * L, D, D], "gemm_tflops": flops_gemm / t_gemm / 1e12, "mode": "tf32" if mode else "fp32"}
+    # cost matrix at BASELINE config 4 (the size its HBM target is stated for)
+    from util import synth_preds, synth_targets
+    rng = np.random.default_rng(0)
+    Bm, T, Q, C, A = 256, 100, 300, 82, 3
+    tr = synth_targets(rng, Bm, T, C, A); pr = synth_preds(rng, Bm, Q, C, A)
+    d = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (*tr, *pr)]
+    cost = torch.empty(Bm, T, Q, device="cuda")
+    t_cost = time_kernel(lambda: _lib.call("bdetr_cost_matrix_fwd", Bm, T, Q, C, A, ptr(d[0]), ptr(d[1]), ptr(d[2]), ptr(d[4]), ptr(d[5]), ptr(d[6]),
+                                           1000.0, 1.0, 1.0, ptr(cost), stream_ptr()), reps=20, flush=flush)
+    bytes_cost = 4.0 * Bm * (Q * C + Q * A + 4 * Q + T * C + T * A + 4 * T + T * Q)
+    tpeak = peaks.get("bf16_tflops", 1590.0)
+    hpeak = peaks.get("hbm_gbs", 6650.0)
+    src = "MEASURED_PEAKS.json (burst figures, kernel timed alone)" if peaks else "fallback 1590 TFLOP/s / 6650 GB/s"
+    ach = flops_gemm / t_gemm / 1e12
+    return {"bound": "tensor", "kernel": "gemm_umma_kernel (Dense forward [%d,%d]x[%d,%d], tf32 operands)" % (M, D, D, D) if mode else
+            "gemm_simt_kernel (Dense forward [%d,%d]x[%d,%d], fp32 FFMA)" % (M, D, D, D),
+            "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None, "peak_source": src,
+            "us_per_launch": t_gemm * 1e6, "mode": "tf32" if mode else "fp32",
+            "note": "peak is the measured bf16 cuBLAS figure; TF32 tensor peak is half of it. K=256 makes this GEMM "
+                    "latency / L2-ingest bound (see profiles/README.md)",
+            "other_kernels": {
+                "attention_core_fwd": {"bound": "tensor", "achieved": flops_attn / t_attn / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                                       "frac": flops_attn / t_attn / 1e12 / tpeak, "us_per_launch": t_attn * 1e6, "shape": [B, H, L, L]},
+                "cost_matrix_fwd_config4": {"bound": "hbm", "achieved": bytes_cost / t_cost / 1e9, "peak": hpeak, "unit": "GB/s",
+                                            "frac": bytes_cost / t_cost / 1e9 / hpeak, "us_per_launch": t_cost * 1e6,
+                                            "algorithmic_bytes": bytes_cost}}}
 
 
 def cpu_reference_steps(cfg, B, C, A, steps, warmup, threads):

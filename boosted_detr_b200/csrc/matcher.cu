@@ -138,10 +138,11 @@ __device__ __forceinline__ float focal0(float pc)
 // ---------------------------------------------------------------------------------------------
 constexpr int CM_QT = 64;
 constexpr int CM_THREADS = 256;
+constexpr int CM_TB = 10;        // floats kept per target box: ymin,xmin,ymax,xmax, area, 10*(ymin,xmin,ymax,xmax), nan flag
 
 struct CostSmemLayout {
     int Cs, As, CW, AW;
-    size_t off_nlc, off_df, off_s0, off_tbox, off_cbits, off_abits, bytes;
+    size_t off_nlc, off_df, off_s0, off_tbox, off_cstar, off_cbits, off_abits, bytes;
 };
 
 static CostSmemLayout cost_smem_layout(int T, int C, int A, bool has_attr)
@@ -152,11 +153,44 @@ static CostSmemLayout cost_smem_layout(int T, int C, int A, bool has_attr)
     L.off_nlc = o; o += sizeof(float) * CM_QT * L.Cs;
     L.off_df = o; if (has_attr) o += sizeof(float) * CM_QT * L.As;
     L.off_s0 = o; o += sizeof(float) * CM_QT;
-    L.off_tbox = o; o += sizeof(float) * 4 * T;
+    L.off_tbox = o; o += sizeof(float) * CM_TB * T;
+    L.off_cstar = o; o += sizeof(int) * T;
     L.off_cbits = o; o += sizeof(uint32_t) * T * L.CW;
     L.off_abits = o; if (has_attr) o += sizeof(uint32_t) * T * L.AW;
     L.bytes = o;
     return L;
+}
+
+// Box term with the per-box invariants (areas, 10x coordinates) hoisted; same unfused arithmetic as
+// box_pair_cost, so the bits are identical.  NaN inputs are handled by the caller (flag), which lets the
+// min/max use the plain NaN-suppressing instructions.
+__device__ __forceinline__ float box_pair_cost_pre(const float *__restrict__ t, const float (&p)[9])
+{
+    const float iy0 = fmaxf(t[0], p[0]), ix0 = fmaxf(t[1], p[1]);
+    const float iy1 = fminf(t[2], p[2]), ix1 = fminf(t[3], p[3]);
+    const float iw = fmaxf(0.0f, __fsub_rn(ix1, ix0)), ih = fmaxf(0.0f, __fsub_rn(iy1, iy0));
+    const float ai = __fmul_rn(iw, ih);
+    const float un = __fsub_rn(__fadd_rn(t[4], p[4]), ai);
+    const float iou = div_no_nan(ai, un);
+    const float ey0 = fminf(t[0], p[0]), ex0 = fminf(t[1], p[1]);
+    const float ey1 = fmaxf(t[2], p[2]), ex1 = fmaxf(t[3], p[3]);
+    const float ew = fmaxf(0.0f, __fsub_rn(ex1, ex0)), eh = fmaxf(0.0f, __fsub_rn(ey1, ey0));
+    const float ae = __fmul_rn(ew, eh);
+    const float giou = __fsub_rn(iou, div_no_nan(__fsub_rn(ae, un), ae));
+    const float d0 = __fsub_rn(t[5], p[5]), d1 = __fsub_rn(t[6], p[6]), d2 = __fsub_rn(t[7], p[7]), d3 = __fsub_rn(t[8], p[8]);
+    const float ss = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
+    const float l2 = __fmul_rn(ss, 0.25f);                      // == ss / 4 exactly
+    return __fadd_rn(__fmul_rn(2.0f, __fsub_rn(1.0f, giou)), __fmul_rn(5.0f, l2));
+}
+__device__ __forceinline__ void box_invariants(float x, float y, float w, float h, float out[CM_TB])
+{
+    const BoxTF b = coco_to_tf(x, y, w, h);
+    out[0] = b.ymin; out[1] = b.xmin; out[2] = b.ymax; out[3] = b.xmax;
+    const float bw = fmaxf(0.0f, __fsub_rn(b.xmax, b.xmin)), bh = fmaxf(0.0f, __fsub_rn(b.ymax, b.ymin));
+    out[4] = __fmul_rn(bw, bh);
+    out[5] = __fmul_rn(10.0f, b.ymin); out[6] = __fmul_rn(10.0f, b.xmin);
+    out[7] = __fmul_rn(10.0f, b.ymax); out[8] = __fmul_rn(10.0f, b.xmax);
+    out[9] = (x != x || y != y || w != w || h != h) ? 1.0f : 0.0f;
 }
 
 template <bool HAS_ATTR>
@@ -172,53 +206,59 @@ cost_matrix_kernel(int T, int Q, int C, int A,
     float *dfs = reinterpret_cast<float *>(smem_raw + L.off_df);
     float *s0 = reinterpret_cast<float *>(smem_raw + L.off_s0);
     float *tbox = reinterpret_cast<float *>(smem_raw + L.off_tbox);
+    int *cstar = reinterpret_cast<int *>(smem_raw + L.off_cstar);
     uint32_t *cbits = reinterpret_cast<uint32_t *>(smem_raw + L.off_cbits);
     uint32_t *abits = reinterpret_cast<uint32_t *>(smem_raw + L.off_abits);
 
     const int b = blockIdx.y, q0 = blockIdx.x * CM_QT, nq = min(CM_QT, Q - q0), tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int Cs = L.Cs, As = L.As, CW = L.CW, AW = L.AW;
 
-    for (int e = tid; e < T * CW; e += CM_THREADS) cbits[e] = 0u;
-    if (HAS_ATTR) for (int e = tid; e < T * AW; e += CM_THREADS) abits[e] = 0u;
-    __syncthreads();
-
-    // target side: class / attribute bit sets and converted boxes
+    // ---- target side: one warp per row builds the class / attribute bit sets with ballots (coalesced reads,
+    //      no divisions, no atomics) and notes the single class of a one-hot row ----
     const float *ct = cat_true + (size_t)b * T * C;
-    for (int e = tid; e < T * C; e += CM_THREADS) {
-        if (ct[e] != 0.0f) { const int t = e / C, c = e - t * C; atomicOr(&cbits[t * CW + (c >> 5)], 1u << (c & 31)); }
-    }
-    if (HAS_ATTR) {
-        const float *atp = attr_true + (size_t)b * T * A;
-        for (int e = tid; e < T * A; e += CM_THREADS) {
-            if (atp[e] != 0.0f) { const int t = e / A, a = e - t * A; atomicOr(&abits[t * AW + (a >> 5)], 1u << (a & 31)); }
+    for (int t = warp; t < T; t += CM_THREADS / 32) {
+        int nset = 0, first = -1;
+        for (int w = 0; w < CW; ++w) {
+            const int c = (w << 5) + lane;
+            const uint32_t bits = __ballot_sync(0xffffffffu, c < C && ct[(size_t)t * C + c] != 0.0f);
+            if (lane == 0) cbits[t * CW + w] = bits;
+            if (bits && first < 0) first = (w << 5) + __ffs(bits) - 1;
+            nset += __popc(bits);
+        }
+        if (lane == 0) cstar[t] = nset == 1 ? first : -1;
+        if (HAS_ATTR) {
+            const float *atp = attr_true + ((size_t)b * T + t) * A;
+            for (int w = 0; w < AW; ++w) {
+                const int a = (w << 5) + lane;
+                const uint32_t bits = __ballot_sync(0xffffffffu, a < A && atp[a] != 0.0f);
+                if (lane == 0) abits[t * AW + w] = bits;
+            }
         }
     }
     for (int t = tid; t < T; t += CM_THREADS) {
         const float4 bx = reinterpret_cast<const float4 *>(box_true)[(size_t)b * T + t];
-        const BoxTF tb = coco_to_tf(bx.x, bx.y, bx.z, bx.w);
-        tbox[4 * t + 0] = tb.ymin; tbox[4 * t + 1] = tb.xmin; tbox[4 * t + 2] = tb.ymax; tbox[4 * t + 3] = tb.xmax;
+        float inv[CM_TB];
+        box_invariants(bx.x, bx.y, bx.z, bx.w, inv);
+#pragma unroll
+        for (int k = 0; k < CM_TB; ++k) tbox[t * CM_TB + k] = inv[k];
     }
-    // prediction side: mean-over-C'd  -log(clip(p)+eps)  per (column, class)
-    const float *cp = cat_pred + ((size_t)b * Q + q0) * C;
-    const float fC = (float)C;
-    for (int e = tid; e < nq * C; e += CM_THREADS) {
-        const int q = e / C, c = e - q * C;
-        nlc[q * Cs + c] = __fdiv_rn(neg_log_clip(cp[e]), fC);
-    }
-    if (HAS_ATTR) {
-        const float *ap = attr_pred + ((size_t)b * Q + q0) * A;
-        for (int e = tid; e < nq * A; e += CM_THREADS) {
-            const int q = e / A, a = e - q * A;
-            const float pc = safe_clip(ap[e]);
-            const float f0 = focal0(pc);
-            dfs[q * As + a] = __fsub_rn(focal1(pc), f0);
-            // keep f0 for the row sum below (reuse global read: recomputed there to keep smem small)
-        }
-        __syncthreads();
-        for (int q = tid; q < nq; q += CM_THREADS) {
+    // ---- prediction side: one warp per column; mean-over-C'd  -log(clip(p)+eps)  per class, focal terms ----
+    const float fC = (float)C, fA = (float)A;
+    for (int q = warp; q < nq; q += CM_THREADS / 32) {
+        const float *cp = cat_pred + ((size_t)b * Q + q0 + q) * C;
+        for (int c = lane; c < C; c += 32) nlc[q * Cs + c] = __fdiv_rn(neg_log_clip(cp[c]), fC);
+        if (HAS_ATTR) {
+            const float *ap = attr_pred + ((size_t)b * Q + q0 + q) * A;
             float s = 0.0f;
-            for (int a = 0; a < A; ++a) s = __fadd_rn(s, focal0(safe_clip(ap[q * A + a])));
-            s0[q] = s;
+            for (int a = lane; a < A; a += 32) {
+                const float pc = safe_clip(ap[a]);
+                const float f0 = focal0(pc);
+                dfs[q * As + a] = __fsub_rn(focal1(pc), f0);
+                s += f0;
+            }
+            s = warp_sum(s);
+            if (lane == 0) s0[q] = s;
         }
     }
     __syncthreads();
@@ -227,21 +267,33 @@ cost_matrix_kernel(int T, int Q, int C, int A,
     if (qi >= nq) return;
     const int q = q0 + qi;
     const float4 pb = reinterpret_cast<const float4 *>(box_pred)[(size_t)b * Q + q];
-    const BoxTF p = coco_to_tf(pb.x, pb.y, pb.z, pb.w);
+    float pinv[CM_TB];
+    box_invariants(pb.x, pb.y, pb.z, pb.w, pinv);
+    float p9[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) p9[k] = pinv[k];
+    const bool pnan = pinv[9] != 0.0f;
     const float *my_nl = nlc + qi * Cs;
     const float *my_df = dfs + qi * As;
     const float my_s0 = HAS_ATTR ? s0[qi] : 0.0f;
-    const float fA = (float)A;
     float *out = cost + (size_t)b * T * Q + q;
 
+#pragma unroll 2
     for (int t = tg; t < T; t += CM_THREADS / CM_QT) {
-        float cat = 0.0f;
-        for (int w = 0; w < CW; ++w) {
-            uint32_t bits = cbits[t * CW + w];
-            while (bits) { const int c = __ffs(bits) - 1; bits &= bits - 1; cat = __fadd_rn(cat, my_nl[(w << 5) + c]); }
+        float cat;
+        const int cs = cstar[t];
+        if (cs >= 0) {
+            cat = __fadd_rn(0.0f, my_nl[cs]);                       // one-hot row: a single gather
+        } else {
+            cat = 0.0f;
+            for (int w = 0; w < CW; ++w) {
+                uint32_t bits = cbits[t * CW + w];
+                while (bits) { const int c = __ffs(bits) - 1; bits &= bits - 1; cat = __fadd_rn(cat, my_nl[(w << 5) + c]); }
+            }
         }
-        BoxTF tb; tb.ymin = tbox[4 * t]; tb.xmin = tbox[4 * t + 1]; tb.ymax = tbox[4 * t + 2]; tb.xmax = tbox[4 * t + 3];
-        const float box = box_pair_cost(tb, p, nullptr);
+        const float *tb = tbox + t * CM_TB;
+        float box = box_pair_cost_pre(tb, p9);
+        if (pnan || tb[9] != 0.0f) box = CUDART_NAN_F;              // tf.maximum / minimum propagate NaN
         float v = __fadd_rn(__fmul_rn(w_cat, cat), __fmul_rn(w_box, box));
         if (HAS_ATTR) {
             float s = my_s0;
@@ -322,14 +374,29 @@ lsap_kernel(int T, int Q, const float *__restrict__ cost, const int32_t *__restr
             double best_s = CUDART_INF;
             int best_rank = -1;
             const float *crow = tr ? (cb + i) : (cb + (size_t)i * Q);
-            for (int it = lane; it < nrem; it += 32) {
-                const int j = remaining[it];
-                const double c = (double)(tr ? crow[(size_t)j * Q] : crow[j]);
-                const double r = ((minVal + c) - ui) - v[j];
-                double s = spc[j];
-                if (r < s) { path[j] = i; spc[j] = r; s = r; }
-                const int rank = (row4col[j] == -1) ? (RANK_FREE + it) : (RANK_USED - it);
-                if (s < best_s || (s == best_s && rank > best_rank)) { best_s = s; best_rank = rank; }
+            // The column scan, 8 strided positions per lane at a time: all cost loads of a group are issued
+            // before any of them is used (one L2 round trip per group instead of one per column).
+            for (int base = lane; base < nrem; base += 32 * 8) {
+                int jj[8];
+                float cc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int it = base + 32 * k;
+                    jj[k] = it < nrem ? remaining[it] : -1;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) cc[k] = jj[k] >= 0 ? (tr ? crow[(size_t)jj[k] * Q] : crow[jj[k]]) : 0.0f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int j = jj[k];
+                    if (j < 0) continue;
+                    const int it = base + 32 * k;
+                    const double r = ((minVal + (double)cc[k]) - ui) - v[j];
+                    double s = spc[j];
+                    if (r < s) { path[j] = i; spc[j] = r; s = r; }
+                    const int rank = (row4col[j] == -1) ? (RANK_FREE + it) : (RANK_USED - it);
+                    if (s < best_s || (s == best_s && rank > best_rank)) { best_s = s; best_rank = rank; }
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
