@@ -136,19 +136,34 @@ __device__ __forceinline__ float focal0(float pc)
 // K7: cost matrix.  CTA = (image b, tile of QT prediction columns); thread = one column, looping
 // over a quarter of the target rows, so each warp stores 128 contiguous bytes per row.
 // ---------------------------------------------------------------------------------------------
+// a / b for normal, non-zero b: reciprocal estimate refined by Newton steps with exact FMA residuals -- the fast
+// path every IEEE-division expansion takes, without its range checks and slow-path call (the operands here are
+// box areas / class counts).  Rounds like a true division except in vanishingly rare double-rounding cases.
+__device__ __forceinline__ float div_rn_fast(float a, float b)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    r = fmaf(fmaf(-b, r, 1.0f), r, r);
+    const float q = __fmul_rn(a, r);
+    return fmaf(fmaf(-b, q, a), r, q);
+}
+__device__ __forceinline__ float div_no_nan_fast(float a, float b) { return b == 0.0f ? 0.0f : div_rn_fast(a, b); }
+
 constexpr int CM_QT = 64;
-constexpr int CM_THREADS = 256;
-constexpr int CM_TB = 10;        // floats kept per target box: ymin,xmin,ymax,xmax, area, 10*(ymin,xmin,ymax,xmax), nan flag
+constexpr int CM_THREADS = 512;
+constexpr int CM_TB = 12;        // floats kept per target box: ymin,xmin,ymax,xmax | area, 10*ymin,10*xmin,10*ymax | 10*xmax, nan flag, pad
 
 struct CostSmemLayout {
     int Cs, As, CW, AW;
+    uint32_t magicC, magicA;      // e / C == __umulhi(e, magicC) for e < 2^20 (exact: magic = ceil(2^32 / C))
     size_t off_nlc, off_df, off_s0, off_tbox, off_cstar, off_cbits, off_abits, bytes;
 };
 
 static CostSmemLayout cost_smem_layout(int T, int C, int A, bool has_attr)
 {
     CostSmemLayout L;
-    L.Cs = C | 1; L.As = A | 1; L.CW = (C + 31) / 32; L.AW = (A + 31) / 32;
+    L.Cs = C; L.As = A; L.CW = (C + 31) / 32; L.AW = (A + 31) / 32;      // flat copies: the gather stride C is at worst 2-way conflicted
+    L.magicC = (uint32_t)((0x100000000ull + C - 1) / C); L.magicA = (uint32_t)((0x100000000ull + A - 1) / A);
     size_t o = 0;
     L.off_nlc = o; o += sizeof(float) * CM_QT * L.Cs;
     L.off_df = o; if (has_attr) o += sizeof(float) * CM_QT * L.As;
@@ -164,19 +179,19 @@ static CostSmemLayout cost_smem_layout(int T, int C, int A, bool has_attr)
 // Box term with the per-box invariants (areas, 10x coordinates) hoisted; same unfused arithmetic as
 // box_pair_cost, so the bits are identical.  NaN inputs are handled by the caller (flag), which lets the
 // min/max use the plain NaN-suppressing instructions.
-__device__ __forceinline__ float box_pair_cost_pre(const float *__restrict__ t, const float (&p)[9])
+__device__ __forceinline__ float box_pair_cost_pre(const float (&t)[CM_TB], const float (&p)[9])
 {
     const float iy0 = fmaxf(t[0], p[0]), ix0 = fmaxf(t[1], p[1]);
     const float iy1 = fminf(t[2], p[2]), ix1 = fminf(t[3], p[3]);
     const float iw = fmaxf(0.0f, __fsub_rn(ix1, ix0)), ih = fmaxf(0.0f, __fsub_rn(iy1, iy0));
     const float ai = __fmul_rn(iw, ih);
     const float un = __fsub_rn(__fadd_rn(t[4], p[4]), ai);
-    const float iou = div_no_nan(ai, un);
+    const float iou = div_no_nan_fast(ai, un);
     const float ey0 = fminf(t[0], p[0]), ex0 = fminf(t[1], p[1]);
     const float ey1 = fmaxf(t[2], p[2]), ex1 = fmaxf(t[3], p[3]);
     const float ew = fmaxf(0.0f, __fsub_rn(ex1, ex0)), eh = fmaxf(0.0f, __fsub_rn(ey1, ey0));
     const float ae = __fmul_rn(ew, eh);
-    const float giou = __fsub_rn(iou, div_no_nan(__fsub_rn(ae, un), ae));
+    const float giou = __fsub_rn(iou, div_no_nan_fast(__fsub_rn(ae, un), ae));
     const float d0 = __fsub_rn(t[5], p[5]), d1 = __fsub_rn(t[6], p[6]), d2 = __fsub_rn(t[7], p[7]), d3 = __fsub_rn(t[8], p[8]);
     const float ss = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
     const float l2 = __fmul_rn(ss, 0.25f);                      // == ss / 4 exactly
@@ -191,6 +206,7 @@ __device__ __forceinline__ void box_invariants(float x, float y, float w, float 
     out[5] = __fmul_rn(10.0f, b.ymin); out[6] = __fmul_rn(10.0f, b.xmin);
     out[7] = __fmul_rn(10.0f, b.ymax); out[8] = __fmul_rn(10.0f, b.xmax);
     out[9] = (x != x || y != y || w != w || h != h) ? 1.0f : 0.0f;
+    out[10] = 0.0f; out[11] = 0.0f;
 }
 
 template <bool HAS_ATTR>
@@ -210,30 +226,24 @@ cost_matrix_kernel(int T, int Q, int C, int A,
     uint32_t *cbits = reinterpret_cast<uint32_t *>(smem_raw + L.off_cbits);
     uint32_t *abits = reinterpret_cast<uint32_t *>(smem_raw + L.off_abits);
 
-    const int b = blockIdx.y, q0 = blockIdx.x * CM_QT, nq = min(CM_QT, Q - q0), tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int Cs = L.Cs, As = L.As, CW = L.CW, AW = L.AW;
 
-    // ---- target side: one warp per row builds the class / attribute bit sets with ballots (coalesced reads,
-    //      no divisions, no atomics) and notes the single class of a one-hot row ----
+    // ---- target side: flat, division-free scans (independent loads, unrolled by the compiler) ----
+    for (int e = tid; e < T * CW; e += CM_THREADS) cbits[e] = 0u;
+    if (HAS_ATTR) for (int e = tid; e < T * AW; e += CM_THREADS) abits[e] = 0u;
+    __syncthreads();
     const float *ct = cat_true + (size_t)b * T * C;
-    for (int t = warp; t < T; t += CM_THREADS / 32) {
-        int nset = 0, first = -1;
-        for (int w = 0; w < CW; ++w) {
-            const int c = (w << 5) + lane;
-            const uint32_t bits = __ballot_sync(0xffffffffu, c < C && ct[(size_t)t * C + c] != 0.0f);
-            if (lane == 0) cbits[t * CW + w] = bits;
-            if (bits && first < 0) first = (w << 5) + __ffs(bits) - 1;
-            nset += __popc(bits);
-        }
-        if (lane == 0) cstar[t] = nset == 1 ? first : -1;
-        if (HAS_ATTR) {
-            const float *atp = attr_true + ((size_t)b * T + t) * A;
-            for (int w = 0; w < AW; ++w) {
-                const int a = (w << 5) + lane;
-                const uint32_t bits = __ballot_sync(0xffffffffu, a < A && atp[a] != 0.0f);
-                if (lane == 0) abits[t * AW + w] = bits;
-            }
+#pragma unroll 4
+    for (int e = tid; e < T * C; e += CM_THREADS) {
+        if (ct[e] != 0.0f) { const int t = __umulhi((uint32_t)e, L.magicC), c = e - t * C; atomicOr(&cbits[t * CW + (c >> 5)], 1u << (c & 31)); }
+    }
+    if (HAS_ATTR) {
+        const float *atp = attr_true + (size_t)b * T * A;
+#pragma unroll 4
+        for (int e = tid; e < T * A; e += CM_THREADS) {
+            if (atp[e] != 0.0f) { const int t = __umulhi((uint32_t)e, L.magicA), a = e - t * A; atomicOr(&abits[t * AW + (a >> 5)], 1u << (a & 31)); }
         }
     }
     for (int t = tid; t < T; t += CM_THREADS) {
@@ -241,71 +251,109 @@ cost_matrix_kernel(int T, int Q, int C, int A,
         float inv[CM_TB];
         box_invariants(bx.x, bx.y, bx.z, bx.w, inv);
 #pragma unroll
-        for (int k = 0; k < CM_TB; ++k) tbox[t * CM_TB + k] = inv[k];
+        for (int k = 0; k < CM_TB; k += 4)
+            *reinterpret_cast<float4 *>(tbox + t * CM_TB + k) = make_float4(inv[k], inv[k + 1], inv[k + 2], inv[k + 3]);
     }
-    // ---- prediction side: one warp per column; mean-over-C'd  -log(clip(p)+eps)  per class, focal terms ----
     const float fC = (float)C, fA = (float)A;
-    for (int q = warp; q < nq; q += CM_THREADS / 32) {
-        const float *cp = cat_pred + ((size_t)b * Q + q0 + q) * C;
-        for (int c = lane; c < C; c += 32) nlc[q * Cs + c] = __fdiv_rn(neg_log_clip(cp[c]), fC);
-        if (HAS_ATTR) {
-            const float *ap = attr_pred + ((size_t)b * Q + q0 + q) * A;
-            float s = 0.0f;
-            for (int a = lane; a < A; a += 32) {
-                const float pc = safe_clip(ap[a]);
-                const float f0 = focal0(pc);
-                dfs[q * As + a] = __fsub_rn(focal1(pc), f0);
-                s += f0;
-            }
-            s = warp_sum(s);
-            if (lane == 0) s0[q] = s;
-        }
-    }
-    __syncthreads();
+    const bool small_attr = HAS_ATTR && A <= 8;                 // branch-free attribute sum for tiny vocabularies
 
-    const int qi = tid % CM_QT, tg = tid / CM_QT;
-    if (qi >= nq) return;
-    const int q = q0 + qi;
-    const float4 pb = reinterpret_cast<const float4 *>(box_pred)[(size_t)b * Q + q];
-    float pinv[CM_TB];
-    box_invariants(pb.x, pb.y, pb.z, pb.w, pinv);
-    float p9[9];
+    // ---- column tiles of this image handled by this CTA ----
+    for (int q0 = blockIdx.x * CM_QT; q0 < Q; q0 += gridDim.x * CM_QT) {
+        const int nq = min(CM_QT, Q - q0);
+        __syncthreads();                                        // bit sets complete / previous tile's readers done
+        if (q0 == blockIdx.x * CM_QT) {                         // first tile: single class of one-hot rows
+            for (int t = tid; t < T; t += CM_THREADS) {
+                int nset = 0, first = -1;
+                for (int w = 0; w < CW; ++w) {
+                    const uint32_t bits = cbits[t * CW + w];
+                    if (bits && first < 0) first = (w << 5) + __ffs(bits) - 1;
+                    nset += __popc(bits);
+                }
+                cstar[t] = nset == 1 ? first : -1;
+            }
+        }
+        // prediction side: flat elementwise transforms of the tile (contiguous in HBM)
+        const float *cp = cat_pred + ((size_t)b * Q + q0) * C;
+#pragma unroll 4
+        for (int e = tid; e < nq * C; e += CM_THREADS) nlc[e] = div_rn_fast(neg_log_clip(cp[e]), fC);
+        if (HAS_ATTR) {
+            const float *ap = attr_pred + ((size_t)b * Q + q0) * A;
+#pragma unroll 4
+            for (int e = tid; e < nq * A; e += CM_THREADS) {
+                const float pc = safe_clip(ap[e]);
+                dfs[e] = __fsub_rn(focal1(pc), focal0(pc));
+            }
+            // row sums of the y = 0 focal term: one warp per column
+            for (int q = warp; q < nq; q += CM_THREADS / 32) {
+                float sacc = 0.0f;
+                for (int a = lane; a < A; a += 32) sacc += focal0(safe_clip(ap[q * A + a]));
+                sacc = warp_sum(sacc);
+                if (lane == 0) s0[q] = sacc;
+            }
+        }
+        __syncthreads();
+
+        const int qi = tid % CM_QT, tg = tid / CM_QT;
+        if (qi < nq) {
+            const int q = q0 + qi;
+            const float4 pb = reinterpret_cast<const float4 *>(box_pred)[(size_t)b * Q + q];
+            float pinv[CM_TB];
+            box_invariants(pb.x, pb.y, pb.z, pb.w, pinv);
+            float p9[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) p9[k] = pinv[k];
-    const bool pnan = pinv[9] != 0.0f;
-    const float *my_nl = nlc + qi * Cs;
-    const float *my_df = dfs + qi * As;
-    const float my_s0 = HAS_ATTR ? s0[qi] : 0.0f;
-    float *out = cost + (size_t)b * T * Q + q;
+            for (int k = 0; k < 9; ++k) p9[k] = pinv[k];
+            const bool pnan = pinv[9] != 0.0f;
+            const float *my_nl = nlc + qi * Cs;
+            const float *my_df = dfs + qi * As;
+            const float my_s0 = HAS_ATTR ? s0[qi] : 0.0f;
+            float dfr[8];
+            if (small_attr) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) dfr[a] = a < A ? my_df[a] : 0.0f;
+            }
+            float *out = cost + (size_t)b * T * Q + q;
 
 #pragma unroll 2
-    for (int t = tg; t < T; t += CM_THREADS / CM_QT) {
-        float cat;
-        const int cs = cstar[t];
-        if (cs >= 0) {
-            cat = __fadd_rn(0.0f, my_nl[cs]);                       // one-hot row: a single gather
-        } else {
-            cat = 0.0f;
-            for (int w = 0; w < CW; ++w) {
-                uint32_t bits = cbits[t * CW + w];
-                while (bits) { const int c = __ffs(bits) - 1; bits &= bits - 1; cat = __fadd_rn(cat, my_nl[(w << 5) + c]); }
+            for (int t = tg; t < T; t += CM_THREADS / CM_QT) {
+                float cat;
+                const int cs = cstar[t];
+                if (cs >= 0) {
+                    cat = __fadd_rn(0.0f, my_nl[cs]);               // one-hot row: a single gather
+                } else {
+                    cat = 0.0f;
+                    for (int w = 0; w < CW; ++w) {
+                        uint32_t bits = cbits[t * CW + w];
+                        while (bits) { const int c = __ffs(bits) - 1; bits &= bits - 1; cat = __fadd_rn(cat, my_nl[(w << 5) + c]); }
+                    }
+                }
+                float tb[CM_TB];
+#pragma unroll
+                for (int k = 0; k < CM_TB; k += 4) {
+                    const float4 v4 = *reinterpret_cast<const float4 *>(tbox + t * CM_TB + k);
+                    tb[k] = v4.x; tb[k + 1] = v4.y; tb[k + 2] = v4.z; tb[k + 3] = v4.w;
+                }
+                float box = box_pair_cost_pre(tb, p9);
+                if (pnan || tb[9] != 0.0f) box = CUDART_NAN_F;      // tf.maximum / minimum propagate NaN
+                float v = __fadd_rn(__fmul_rn(w_cat, cat), __fmul_rn(w_box, box));
+                if (HAS_ATTR) {
+                    float sa = my_s0;
+                    if (small_attr) {
+                        const uint32_t bits = abits[t * AW];
+#pragma unroll
+                        for (int a = 0; a < 8; ++a) sa = __fadd_rn(sa, (bits >> a) & 1u ? dfr[a] : 0.0f);   // + 0.0f is exact
+                    } else {
+                        for (int w = 0; w < AW; ++w) {
+                            uint32_t bits = abits[t * AW + w];
+                            while (bits) { const int a = __ffs(bits) - 1; bits &= bits - 1; sa = __fadd_rn(sa, my_df[(w << 5) + a]); }
+                        }
+                    }
+                    v = __fadd_rn(v, __fmul_rn(w_attr, div_rn_fast(sa, fA)));
+                } else {
+                    v = __fadd_rn(v, 0.0f);
+                }
+                out[(size_t)t * Q] = v;
             }
         }
-        const float *tb = tbox + t * CM_TB;
-        float box = box_pair_cost_pre(tb, p9);
-        if (pnan || tb[9] != 0.0f) box = CUDART_NAN_F;              // tf.maximum / minimum propagate NaN
-        float v = __fadd_rn(__fmul_rn(w_cat, cat), __fmul_rn(w_box, box));
-        if (HAS_ATTR) {
-            float s = my_s0;
-            for (int w = 0; w < AW; ++w) {
-                uint32_t bits = abits[t * AW + w];
-                while (bits) { const int a = __ffs(bits) - 1; bits &= bits - 1; s = __fadd_rn(s, my_df[(w << 5) + a]); }
-            }
-            v = __fadd_rn(v, __fmul_rn(w_attr, __fdiv_rn(s, fA)));
-        } else {
-            v = __fadd_rn(v, 0.0f);
-        }
-        out[(size_t)t * Q] = v;
     }
 }
 
