@@ -214,7 +214,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("BDETR_MODE", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--mode", default=os.environ.get("BDETR_MODE", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -63,20 +63,20 @@ __global__ void __launch_bounds__(256)
 res_ln_bwd_kernel(int M, const float *__restrict__ d_out, const float *__restrict__ z, const float *__restrict__ mean_i,
                   const float *__restrict__ rstd_i, const float *__restrict__ gamma, float keep_scale, uint32_t thresh,
                   uint32_t key, float *__restrict__ d_resid, int acc_resid, float *__restrict__ d_a,
-                  float *__restrict__ g_gamma, float *__restrict__ g_beta, int round_out)
+                  float *__restrict__ g_gamma, float *__restrict__ g_beta, float *__restrict__ g_bias, int round_out)
 {
     constexpr int D = NV * 128;
     __shared__ float red_g[8][D + 4];
     __shared__ float red_b[8][D + 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    float gg[NV * 4], gb[NV * 4], gam[NV * 4];
+    float gg[NV * 4], gb[NV * 4], gam[NV * 4], gbias[NV * 4];   // gbias: column sums of d_a = bias gradient of the Dense before
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         const float4 g = *reinterpret_cast<const float4 *>(gamma + (k * 32 + lane) * 4);
         gam[4 * k] = g.x; gam[4 * k + 1] = g.y; gam[4 * k + 2] = g.z; gam[4 * k + 3] = g.w;
     }
 #pragma unroll
-    for (int e = 0; e < NV * 4; ++e) { gg[e] = 0.0f; gb[e] = 0.0f; }
+    for (int e = 0; e < NV * 4; ++e) { gg[e] = 0.0f; gb[e] = 0.0f; gbias[e] = 0.0f; }
     for (int row = blockIdx.x * nwarp + warp; row < M; row += gridDim.x * nwarp) {
         const float mean = mean_i[row], rstd = rstd_i[row];
         float xh[NV * 4], dy[NV * 4];
@@ -110,6 +110,7 @@ res_ln_bwd_kernel(int M, const float *__restrict__ d_out, const float *__restric
                 dz[e] = rstd * (dy[idx] - s1 - xh[idx] * s2);
                 da[e] = thresh ? (dropout_keep((uint32_t)(off + e), key, thresh) ? dz[e] * keep_scale : 0.0f) : dz[e];
                 da[e] = maybe_tf32(da[e], round_out);
+                gbias[4 * k + e] += da[e];
             }
             *reinterpret_cast<float4 *>(d_a + off) = make_float4(da[0], da[1], da[2], da[3]);
             if (d_resid) {
@@ -134,6 +135,19 @@ res_ln_bwd_kernel(int M, const float *__restrict__ d_out, const float *__restric
         atomicAdd(&g_gamma[c], a);
         atomicAdd(&g_beta[c], b);
     }
+    if (g_bias) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) red_g[warp][(k * 32 + lane) * 4 + e] = gbias[4 * k + e];
+        __syncthreads();
+        for (int c = threadIdx.x; c < D; c += blockDim.x) {
+            float a = 0.0f;
+            for (int w = 0; w < nwarp; ++w) a += red_g[w][c];
+            atomicAdd(&g_bias[c], a);
+        }
+    }
 }
 
 int launch_res_ln_fwd(int M, int D, const float *resid, float *z, const float *gamma, const float *beta, float eps,
@@ -152,15 +166,15 @@ int launch_res_ln_fwd(int M, int D, const float *resid, float *z, const float *g
 
 int launch_res_ln_bwd(int M, int D, const float *d_out, const float *z, const float *mean, const float *rstd,
                       const float *gamma, float rate, uint32_t key, float *d_resid, int acc_resid, float *d_a,
-                      float *g_gamma, float *g_beta, int round_out, cudaStream_t s)
+                      float *g_gamma, float *g_beta, float *g_bias, int round_out, cudaStream_t s)
 {
     BDETR_REQUIRE(M > 0 && (D == 128 || D == 256 || D == 512), BDETR_E_UNSUPPORTED, "LayerNorm width must be 128, 256 or 512");
     const uint32_t thresh = dropout_threshold(rate);
     const float ks = 1.0f / (1.0f - rate);
     const int grid = min(ceil_div(M, 8), 296);
-    if (D == 128) res_ln_bwd_kernel<1><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, round_out);
-    else if (D == 256) res_ln_bwd_kernel<2><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, round_out);
-    else res_ln_bwd_kernel<4><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, round_out);
+    if (D == 128) res_ln_bwd_kernel<1><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
+    else if (D == 256) res_ln_bwd_kernel<2><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
+    else res_ln_bwd_kernel<4><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
     BDETR_CHECK_LAUNCH("res_ln_bwd_kernel");
     return BDETR_OK;
 }
@@ -327,21 +341,33 @@ bn_bwd_stats_kernel(int M, int Dh, const float *__restrict__ h, const float *__r
 __global__ void __launch_bounds__(256)
 bn_relu_bwd_apply_kernel(int M, int Dh, const float *__restrict__ h, const float *__restrict__ d_hn, const float *__restrict__ gamma,
                          const float *__restrict__ mean_i, const float *__restrict__ rstd_i, const float *__restrict__ acc,
-                         float *__restrict__ d_h, float *__restrict__ g_gamma, float *__restrict__ g_beta, int round_out)
+                         float *__restrict__ d_h, float *__restrict__ g_gamma, float *__restrict__ g_beta,
+                         float *__restrict__ g_bias, int round_out)
 {
+    __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
-    if (c >= Dh) return;
+    if (c >= Dh) {                      // keep the block-wide reduction below convergent
+        if (g_bias) col_reduce8(0.0f, red);
+        return;
+    }
     const float mean = mean_i[c], rstd = rstd_i[c], g = gamma[c];
     const float s1 = acc[c], s2 = acc[Dh + c];
     if (blockIdx.y == 0 && r == 0) { g_gamma[c] += s2; g_beta[c] += s1; }
     const float invM = 1.0f / (float)M;
     const int m0 = blockIdx.y * BN_ROWS, m1 = min(M, m0 + BN_ROWS);
+    float bsum = 0.0f;
     for (int m = m0 + r; m < m1; m += 8) {
         const size_t off = (size_t)m * Dh + c;
         const float hv = h[off];
         const float xh = (hv - mean) * rstd;
         const float dx = g * rstd * (d_hn[off] - s1 * invM - xh * s2 * invM);
-        d_h[off] = hv > 0.0f ? maybe_tf32(dx, round_out) : 0.0f;      // ReLU backward (h is the post-ReLU activation)
+        const float o = hv > 0.0f ? maybe_tf32(dx, round_out) : 0.0f;  // ReLU backward (h is the post-ReLU activation)
+        d_h[off] = o;
+        bsum += o;
+    }
+    if (g_bias) {                       // bias gradient of the Dense in front of the BatchNorm
+        bsum = col_reduce8(bsum, red);
+        if (r == 0) atomicAdd(&g_bias[c], bsum);
     }
 }
 
@@ -361,14 +387,15 @@ int launch_bn_fwd(int M, int Dh, const float *h, const float *gamma, const float
     return BDETR_OK;
 }
 int launch_bn_relu_bwd(int M, int Dh, const float *h, const float *d_hn, const float *gamma, const float *mean,
-                       const float *rstd, float *acc, float *d_h, float *g_gamma, float *g_beta, int round_out, cudaStream_t s)
+                       const float *rstd, float *acc, float *d_h, float *g_gamma, float *g_beta, float *g_bias, int round_out,
+                       cudaStream_t s)
 {
     BDETR_REQUIRE(M > 0 && Dh > 0 && acc, BDETR_E_BAD_SHAPE, "bad BatchNorm arguments");
     dim3 grid(ceil_div(Dh, 32), ceil_div(M, BN_ROWS));
     BDETR_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 2 * Dh, s));
     bn_bwd_stats_kernel<<<grid, 256, 0, s>>>(M, Dh, h, d_hn, mean, rstd, acc);
     BDETR_CHECK_LAUNCH("bn_bwd_stats_kernel");
-    bn_relu_bwd_apply_kernel<<<grid, 256, 0, s>>>(M, Dh, h, d_hn, gamma, mean, rstd, acc, d_h, g_gamma, g_beta, round_out);
+    bn_relu_bwd_apply_kernel<<<grid, 256, 0, s>>>(M, Dh, h, d_hn, gamma, mean, rstd, acc, d_h, g_gamma, g_beta, g_bias, round_out);
     BDETR_CHECK_LAUNCH("bn_relu_bwd_apply_kernel");
     return BDETR_OK;
 }

@@ -76,10 +76,10 @@ API int bdetr_attention_block_bwd(int B, int Lq, int Lk, int D, int H,
     // LayerNorm + residual + dropout: residual gradient goes straight to d_query
     const int rnd = tc_mode();
     TRY(launch_res_ln_bwd(Mq, D, d_out, sv->z, sv->mean, sv->rstd, w->ln_gamma, dropout_rate, dropout_key,
-                          d_query, acc_flags & 1, sc->d_z, gw->ln_gamma, gw->ln_beta, rnd, s));
-    // output projection
+                          d_query, acc_flags & 1, sc->d_z, gw->ln_gamma, gw->ln_beta, gw->bo, rnd, s));
+    // output projection (its bias gradient was fused into the LayerNorm backward above)
     // d_o feeds the tcgen05 attention backward MMAs in tensor-core mode: store it tf32-rounded
-    TRY(linear_bwd(Mq, D, D, sv->o, w->wo, sc->d_z, gw->wo, gw->bo, sc->d_o, 0, nullptr, rnd, s));
+    TRY(linear_bwd(Mq, D, D, sv->o, w->wo, sc->d_z, gw->wo, nullptr, sc->d_o, 0, nullptr, rnd, s));
     TRY(launch_attention_bwd(B, H, Lq, Lk, D / H, sv->qp, sv->kp, sv->vp, sv->o, sv->lse, sc->d_o, sc->delta,
                              sc->d_qp, sc->d_kp, sc->d_vp, rnd, s));
     TRY(linear_bwd(Mq, D, D, query, w->wq, sc->d_qp, gw->wq, gw->bq, d_query, 1, nullptr, 0, s));
@@ -113,9 +113,9 @@ API int bdetr_ffn_block_bwd(int M, int D, const float *x, const bdetr_ffn_params
     cudaStream_t s = as_stream(stream);
     const int rnd = tc_mode();
     TRY(launch_res_ln_bwd(M, D, d_out, sv->z, sv->mean, sv->rstd, w->ln_gamma, dropout_rate, dropout_key,
-                          d_x, accumulate_dx, sc->d_z, gw->ln_gamma, gw->ln_beta, rnd, s));
-    // DenseLinear, then ReLU mask on the way into DenseRelu
-    TRY(linear_bwd(M, D, D, sv->h, w->w2, sc->d_z, gw->w2, gw->b2, sc->d_h, 0, sv->h, rnd, s));
+                          d_x, accumulate_dx, sc->d_z, gw->ln_gamma, gw->ln_beta, gw->b2, rnd, s));
+    // DenseLinear (bias gradient fused above), then ReLU mask on the way into DenseRelu
+    TRY(linear_bwd(M, D, D, sv->h, w->w2, sc->d_z, gw->w2, nullptr, sc->d_h, 0, sv->h, rnd, s));
     TRY(linear_bwd(M, D, D, x, w->w1, sc->d_h, gw->w1, gw->b1, d_x, 1, nullptr, 0, s));
     return BDETR_OK;
 }
@@ -178,7 +178,7 @@ API int bdetr_head_bwd(int M, int D, int Dh, int Nout, int kind, float mult,
     TRY(launch_head_act_bwd(M, Nout, kind, mult, sv->act, d_cum, sc->d_logits, s));
     TRY(linear_bwd(M, Nout, Dh, sv->hn, w->w2, sc->d_logits, gw->w2, gw->b2, sc->d_hn, 0, nullptr, 0, s));
     TRY(launch_bn_relu_bwd(M, Dh, sv->h, sc->d_hn, w->bn_gamma, sv->bn_mean, sv->bn_rstd, sv->bn_acc, sc->d_h, gw->bn_gamma,
-                           gw->bn_beta, tc_mode(), s));
-    TRY(linear_bwd(M, Dh, D, x, w->w1, sc->d_h, gw->w1, gw->b1, d_x, accumulate_dx, nullptr, 0, s));
+                           gw->bn_beta, gw->b1, tc_mode(), s));
+    TRY(linear_bwd(M, Dh, D, x, w->w1, sc->d_h, gw->w1, nullptr, d_x, accumulate_dx, nullptr, 0, s));
     return BDETR_OK;
 }
