@@ -216,6 +216,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("BDETR_MODE", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-conc", action="store_true", help="disable multi-stream concurrency inside the step (A/B timing)")
+    ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch (A/B timing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -253,6 +255,8 @@ def main():
     torch.cuda.set_device(local)
     lib = _lib.load()
     lib.bdetr_set_mode(_lib.MODE_TF32 if args.mode == "tf32" else _lib.MODE_FP32)
+    lib.bdetr_set_pdl(0 if args.no_pdl else 1)
+    lib.bdetr_set_concurrency(0 if args.no_conc else 1)
     model = make_model(cfg)
     DataParallel(model)
     batch = synth_batch(rank, B, C, A, cfg)
@@ -337,7 +341,7 @@ def main():
             "e2e": {"value": B * world / e2e_sec, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_sec * 1e3},
             "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
-            "cuda_graph": not args.no_graph, "loss": logs.get("loss") if isinstance(logs, dict) else None,
+            "cuda_graph": not args.no_graph, "pdl": not args.no_pdl, "concurrent_streams": not args.no_conc, "loss": logs.get("loss") if isinstance(logs, dict) else None,
             "step_algorithmic_tflops": flops / sec_per_step / 1e12, "roofline": roof}
     if not args.no_cpu_baseline and world == 1:
         sec = cpu_reference_steps(cfg, B, C, A, 1, 1, cores)

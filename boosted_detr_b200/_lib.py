@@ -44,6 +44,10 @@ PROTOTYPES = {
     "bdetr_last_error": (c_char_p, []),
     "bdetr_set_mode": (c_int, [I]),
     "bdetr_get_mode": (c_int, []),
+    "bdetr_set_pdl": (c_int, [I]),
+    "bdetr_set_concurrency": (c_int, [I]),
+    "bdetr_get_concurrency": (c_int, []),
+    "bdetr_get_pdl": (c_int, []),
     "bdetr_launch_count": (c_longlong, []),
     "bdetr_reset_launch_count": (None, []),
     "bdetr_cost_matrix_fwd": (c_int, [I, I, I, I, I, P, P, P, P, P, P, F, F, F, P, P]),
@@ -89,6 +93,11 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    # A/B switches for debugging / timing (defaults: both on)
+    if os.environ.get("BDETR_PDL") is not None:
+        lib.bdetr_set_pdl(int(os.environ["BDETR_PDL"]))
+    if os.environ.get("BDETR_CONCURRENCY") is not None:
+        lib.bdetr_set_concurrency(int(os.environ["BDETR_CONCURRENCY"]))
     _lib = lib
     return lib
 

@@ -192,6 +192,15 @@ class BoostedDETR:
             self._side = torch.cuda.Stream()
         return self._side
 
+    def _aux_streams(self):
+        """Three extra streams: two for the attribute / box heads (the three heads of a block are independent
+        chains of short kernels), one for the batch-invariant decoder self-attention."""
+        if not _lib.load().bdetr_get_concurrency():
+            return [torch.cuda.current_stream()] * 3          # A/B switch: everything in order on one stream
+        if getattr(self, "_aux", None) is None:
+            self._aux = [torch.cuda.Stream() for _ in range(3)]
+        return self._aux
+
     # -- forward -------------------------------------------------------------------------------
     def forward(self, feats, y_true, training):
         """The hot loop (reference :199-246).  Returns (y_pred, ctx)."""
@@ -209,6 +218,7 @@ class BoostedDETR:
             _lib.call("bdetr_round_tf32", feats.numel(), ptr(feats), ptr(x), stream_ptr())
         cums = None
         blocks, loss_ctxs = [], []
+        aux = self._aux_streams()
         for i in range(N):
             keys = self._keys(i) if use_dropout else None
             enc = self.EncoderTransformerBlocks[i]
@@ -218,18 +228,37 @@ class BoostedDETR:
             for nm in ("SelfAttentionBlock", "JointAttentionBlock", "FeedForwardBlock"):
                 if hasattr(dec_l, nm):
                     getattr(dec_l, nm).rate = 0.1 if use_dropout else 0.0
+            # Decoder self-attention (blocks >= 1) only sees the learned queries, not the image: it runs on its own
+            # stream underneath the encoder block and is joined in front of the cross-attention.
+            dkeys = keys["dec"] if keys else (0, 0, 0)
+            pre_self, dec0 = None, None
+            # (not on the very first call: layers build lazily in execution order, and the weight-initialisation
+            # order -- hence the seeded initial weights -- must not depend on this scheduling choice)
+            if hasattr(dec_l, "SelfAttentionBlock") and dec_l.SelfAttentionBlock.built:
+                aux[2].wait_stream(main)
+                with torch.cuda.stream(aux[2]):
+                    dec0 = self.DecoderPrep.tile_queries(x.shape[0], like=x)
+                    pre_self = dec_l.SelfAttentionBlock.forward([dec0, dec0, dec0], training, dkeys[0])
             (x, pos), c_enc = enc.forward([x], training, keys["enc"] if keys else None)
-            prep_out, c_prep = self.DecoderPrep.forward([x, pos], training)
-            dec, c_dec = dec_l.forward(list(prep_out), training, keys["dec"] if keys else (0, 0, 0))
+            prep_out, c_prep = self.DecoderPrep.forward([x, pos], training, dec=dec0)
+            if pre_self is not None:
+                main.wait_stream(aux[2])
+            dec, c_dec = dec_l.forward(list(prep_out), training, dkeys, pre_self=pre_self)
             mult = 2.0 if i == 0 else 1.0                 # block 0 is counted twice (reference :222-229)
             if cums is not None and training:
                 cums = [c.clone() for c in cums]          # each block's loss keeps its own running prediction
             heads = (self.CategoryBlocks[i], self.AttributeBlocks[i], self.BoxBlocks[i])
             c_heads, new_cums = [], []
-            for h, head in enumerate(heads):
-                _, c = head.forward([dec], training, cum=None if cums is None else cums[h], mult=mult)
+            for h, head in enumerate(heads):                  # three independent chains: one stream each
+                st = main if h == 0 else aux[h - 1]
+                if st is not main:
+                    st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    _, c = head.forward([dec], training, cum=None if cums is None else cums[h], mult=mult)
                 c_heads.append(c)
                 new_cums.append(c["cum"])
+            main.wait_stream(aux[0])
+            main.wait_stream(aux[1])
             cums = new_cums
             blocks.append({"enc": c_enc, "prep": c_prep, "dec": c_dec, "heads": c_heads})
             if training:
@@ -247,20 +276,41 @@ class BoostedDETR:
         B, T, Q, C, A = first["dims"]
         r_cat, r_attr, r_box = zeros(B, Q, C), zeros(B, Q, A), zeros(B, Q, 4)
         d_x_next = None
+        main = torch.cuda.current_stream()
+        aux = self._aux_streams()
+        keep = []                                            # buffers used on the auxiliary streams stay alive until the final join
         for i in reversed(range(N)):
             blk = ctx["blocks"][i]
             self.loss_fn.backward(ctx["loss"][i], r_cat, r_attr, r_box, gscale)
+            # the three heads are independent: category on the main stream, attribute / box beside it
+            aux[0].wait_stream(main)
+            aux[1].wait_stream(main)
             d_dec = self.CategoryBlocks[i].backward(blk["heads"][0], r_cat)
-            self.AttributeBlocks[i].backward(blk["heads"][1], r_attr, d_x=d_dec, acc=True)
-            self.BoxBlocks[i].backward(blk["heads"][2], r_box, d_x=d_dec, acc=True)
-            d_ev, d_q, d_ek = self.DecoderBlocks[i].backward(blk["dec"], d_dec)
+            with torch.cuda.stream(aux[0]):
+                d_dec_a = self.AttributeBlocks[i].backward(blk["heads"][1], r_attr)
+            with torch.cuda.stream(aux[1]):
+                d_dec_b = self.BoxBlocks[i].backward(blk["heads"][2], r_box)
+            main.wait_stream(aux[0])
+            main.wait_stream(aux[1])
+            accumulate(d_dec_a, d_dec)
+            accumulate(d_dec_b, d_dec)
+            keep += [d_dec_a, d_dec_b]
+            # decoder: FFN + cross-attention on the main stream; the self-attention backward (queries only) and the
+            # query-parameter gradient go to aux[2] underneath the encoder backward
+            d_ev, d_s, d_ek = self.DecoderBlocks[i].backward(blk["dec"], d_dec, defer_self=True)
+            aux[2].wait_stream(main)
+            with torch.cuda.stream(aux[2]):
+                d_q = self.DecoderBlocks[i].backward_self(blk["dec"], d_s)
+                self.DecoderPrep.backward_queries(d_q)
+            keep += [d_s, d_q]
             if d_x_next is not None:
                 accumulate(d_x_next.reshape(d_ev.shape), d_ev)
             enc = self.EncoderTransformerBlocks[i]
             L, D = d_ev.shape[1], d_ev.shape[2]
             g_pos = enc._grads["positional_encoding"].view(L, D)
-            d_x4 = self.DecoderPrep.backward(blk["prep"], d_ev, d_q, d_ek, g_pos)
+            d_x4 = self.DecoderPrep.backward(blk["prep"], d_ev, None, d_ek, g_pos)
             d_x_next = enc.backward(blk["enc"], d_x4)
+        main.wait_stream(aux[2])
         return d_x_next
 
     # -- keras surface -------------------------------------------------------------------------

@@ -2,12 +2,15 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
-#include "common.cuh"
+#include <mutex>
+#include "kernels.cuh"
 
 namespace bdetr {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_mode{BDETR_MODE_FP32};
+static std::atomic<int> g_pdl{1};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 
 void set_error(const char *fmt, ...)
 {
@@ -18,8 +21,80 @@ void set_error(const char *fmt, ...)
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int current_mode() { return g_mode.load(std::memory_order_relaxed); }
+
+// ---- auxiliary stream pool (per device) ---------------------------------------------------------------------
+static std::atomic<int> g_conc{1};
+bool concurrency_enabled() { return g_conc.load(std::memory_order_relaxed) != 0; }
+constexpr int AUX_STREAMS = 9, MAX_DEVICES = 16;
+struct AuxPool {
+    bool ready = false;
+    cudaStream_t st[AUX_STREAMS];
+    cudaEvent_t fork_ev[AUX_STREAMS], join_ev[AUX_STREAMS];
+    int next = 0;
+};
+static AuxPool g_pools[MAX_DEVICES];
+static std::mutex g_pool_mu;
+
+static AuxPool *pool_for_current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return nullptr;
+    AuxPool &p = g_pools[dev];
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!p.ready) {
+        for (int i = 0; i < AUX_STREAMS; ++i) {
+            if (cudaStreamCreateWithFlags(&p.st[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&p.fork_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&p.join_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        p.ready = true;
+    }
+    return &p;
+}
+
+Branches::Branches(cudaStream_t main_stream) : main(main_stream), base(0), used(0), rc(BDETR_OK), on(concurrency_enabled())
+{
+    if (!on) return;
+    AuxPool *p = pool_for_current_device();
+    if (!p) { on = false; return; }
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    base = p->next;                       // rotate so that entry points issued from different caller streams
+    p->next = (p->next + 3) % AUX_STREAMS;   // do not queue behind each other on the same auxiliary stream
+}
+
+cudaStream_t Branches::fork(int i)
+{
+    if (!on) return main;
+    AuxPool *p = pool_for_current_device();
+    const int k = base + i;
+    if (cudaEventRecord(p->fork_ev[k], main) != cudaSuccess || cudaStreamWaitEvent(p->st[k], p->fork_ev[k], 0) != cudaSuccess) {
+        set_error("Branches::fork: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = BDETR_E_CUDA;
+        return main;
+    }
+    used |= 1 << i;
+    return p->st[k];
+}
+
+int Branches::join()
+{
+    if (!on) return rc;
+    AuxPool *p = pool_for_current_device();
+    for (int i = 0; i < 3; ++i) {
+        if (!(used & (1 << i))) continue;
+        const int k = base + i;
+        if (cudaEventRecord(p->join_ev[k], p->st[k]) != cudaSuccess || cudaStreamWaitEvent(main, p->join_ev[k], 0) != cudaSuccess) {
+            set_error("Branches::join: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = BDETR_E_CUDA;
+        }
+    }
+    used = 0;
+    return rc;
+}
 }  // namespace bdetr
 
+extern "C" __attribute__((visibility("default"))) int bdetr_set_concurrency(int on) { bdetr::g_conc.store(on ? 1 : 0); return BDETR_OK; }
+extern "C" __attribute__((visibility("default"))) int bdetr_get_concurrency(void) { return bdetr::g_conc.load(); }
 extern "C" __attribute__((visibility("default"))) int bdetr_version(void) { return 100; }
 extern "C" __attribute__((visibility("default"))) const char *bdetr_last_error(void) { return bdetr::g_err; }
 extern "C" __attribute__((visibility("default"))) int bdetr_set_mode(int mode)
@@ -34,3 +109,5 @@ extern "C" __attribute__((visibility("default"))) int bdetr_set_mode(int mode)
 extern "C" __attribute__((visibility("default"))) int bdetr_get_mode(void) { return bdetr::g_mode.load(); }
 extern "C" __attribute__((visibility("default"))) long long bdetr_launch_count(void) { return bdetr::g_launches.load(); }
 extern "C" __attribute__((visibility("default"))) void bdetr_reset_launch_count(void) { bdetr::g_launches.store(0); }
+extern "C" __attribute__((visibility("default"))) int bdetr_set_pdl(int on) { bdetr::g_pdl.store(on ? 1 : 0); return BDETR_OK; }
+extern "C" __attribute__((visibility("default"))) int bdetr_get_pdl(void) { return bdetr::g_pdl.load(); }

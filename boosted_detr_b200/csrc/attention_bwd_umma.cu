@@ -68,6 +68,9 @@ attention_bwd_dq_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: dependents are released only after this CTA owns its TMEM columns (a dependent that grabbed TMEM first while
+    // blocked in griddepcontrol.wait could starve a late CTA of this grid); global data is touched below the wait.
+    pdl_sync();
     constexpr uint32_t COL_S = 0, COL_DP = 64, COL_DQ = 128;
 
     if (warp == 0) {
@@ -209,6 +212,9 @@ attention_bwd_dkv_umma_kernel(const __grid_constant__ CUtensorMap map_k, const _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: dependents are released only after this CTA owns its TMEM columns (a dependent that grabbed TMEM first while
+    // blocked in griddepcontrol.wait could starve a late CTA of this grid); global data is touched below the wait.
+    pdl_sync();
     constexpr uint32_t COL_S = 0, COL_DP = 64, COL_DK = 128, COL_DV = 160;
     const int orow0 = (b * H + h) * Lq;
 
@@ -364,11 +370,11 @@ int launch_attention_bwd_umma(int B, int H, int Lq, int Lk, int d, const float *
         optin = true;
     }
     dim3 gq(ceil_div(Lq, FB_ROWS), H, B);
-    attention_bwd_dq_umma_kernel<<<gq, FB_THREADS, smem_dq, s>>>(q128, do128, k64, v64, k64mn, H, Lq, Lk, o, d_o, lse, delta, d_qp,
+    launch_k(attention_bwd_dq_umma_kernel, gq, FB_THREADS, smem_dq, s, q128, do128, k64, v64, k64mn, H, Lq, Lk, o, d_o, lse, delta, d_qp,
                                                                 scale, scale_log2, round_out);
     BDETR_CHECK_LAUNCH("attention_bwd_dq_umma_kernel");
     dim3 gk(ceil_div(Lk, FB_ROWS), H, B);
-    attention_bwd_dkv_umma_kernel<<<gk, FB_THREADS, smem_dkv, s>>>(k128, v128, q64, do64, q64mn, do64mn, H, Lq, Lk, lse, delta,
+    launch_k(attention_bwd_dkv_umma_kernel, gk, FB_THREADS, smem_dkv, s, k128, v128, q64, do64, q64mn, do64mn, H, Lq, Lk, lse, delta,
                                                                   d_kp, d_vp, scale, scale_log2, round_out);
     BDETR_CHECK_LAUNCH("attention_bwd_dkv_umma_kernel");
     return BDETR_OK;

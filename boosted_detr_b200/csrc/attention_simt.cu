@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(AT_THREADS)
 attention_fwd_kernel(int H, int Lq, int Lk, const float *__restrict__ qp, const float *__restrict__ kp,
                      const float *__restrict__ vp, float *__restrict__ o, float *__restrict__ lse, float scale_log2, int round_out)
 {
+    pdl_sync();
     __shared__ __align__(16) float Ks[AT_TILE][HD];
     __shared__ __align__(16) float Vs[AT_TILE][HD];
     const int b = blockIdx.z, h = blockIdx.y, D = H * HD;
@@ -123,6 +124,7 @@ attention_bwd_dq_kernel(int H, int Lq, int Lk, const float *__restrict__ qp, con
                         const float *__restrict__ d_o, float *__restrict__ delta, float *__restrict__ d_qp,
                         float scale, float scale_log2, int round_out)
 {
+    pdl_sync();
     __shared__ __align__(16) float Ks[AT_TILE][HD];
     __shared__ __align__(16) float Vs[AT_TILE][HD];
     const int b = blockIdx.z, h = blockIdx.y, D = H * HD;
@@ -174,6 +176,7 @@ attention_bwd_dkv_kernel(int H, int Lq, int Lk, const float *__restrict__ qp, co
                          const float *__restrict__ delta, float *__restrict__ d_kp, float *__restrict__ d_vp,
                          float scale, float scale_log2, int round_out)
 {
+    pdl_sync();
     __shared__ __align__(16) float Qs[AT_TILE][HD];
     __shared__ __align__(16) float Gs[AT_TILE][HD];
     __shared__ float Ls[AT_TILE], Ds[AT_TILE];
@@ -226,7 +229,7 @@ int launch_attention_fwd(int B, int H, int Lq, int Lk, int d, const float *qp, c
         return launch_attention_fwd_umma(B, H, Lq, Lk, d, qp, kp, vp, o, lse, round_out, s);
     const float scale = 1.0f / sqrtf((float)d);
     dim3 grid(ceil_div(Lq, AT_THREADS), H, B);
-    attention_fwd_kernel<<<grid, AT_THREADS, 0, s>>>(H, Lq, Lk, qp, kp, vp, o, lse, scale * LOG2E, round_out);
+    launch_k(attention_fwd_kernel, grid, AT_THREADS, 0, s, H, Lq, Lk, qp, kp, vp, o, lse, scale * LOG2E, round_out);
     BDETR_CHECK_LAUNCH("attention_fwd_kernel");
     return BDETR_OK;
 }
@@ -240,10 +243,10 @@ int launch_attention_bwd(int B, int H, int Lq, int Lk, int d, const float *qp, c
         return launch_attention_bwd_umma(B, H, Lq, Lk, d, qp, kp, vp, o, lse, d_o, delta, d_qp, d_kp, d_vp, round_out, s);
     const float scale = 1.0f / sqrtf((float)d);
     dim3 gq(ceil_div(Lq, AT_THREADS), H, B);
-    attention_bwd_dq_kernel<<<gq, AT_THREADS, 0, s>>>(H, Lq, Lk, qp, kp, vp, o, lse, d_o, delta, d_qp, scale, scale * LOG2E, round_out);
+    launch_k(attention_bwd_dq_kernel, gq, AT_THREADS, 0, s, H, Lq, Lk, qp, kp, vp, o, lse, d_o, delta, d_qp, scale, scale * LOG2E, round_out);
     BDETR_CHECK_LAUNCH("attention_bwd_dq_kernel");
     dim3 gk(ceil_div(Lk, AT_THREADS), H, B);
-    attention_bwd_dkv_kernel<<<gk, AT_THREADS, 0, s>>>(H, Lq, Lk, qp, kp, vp, lse, d_o, delta, d_kp, d_vp, scale, scale * LOG2E, round_out);
+    launch_k(attention_bwd_dkv_kernel, gk, AT_THREADS, 0, s, H, Lq, Lk, qp, kp, vp, lse, d_o, delta, d_kp, d_vp, scale, scale * LOG2E, round_out);
     BDETR_CHECK_LAUNCH("attention_bwd_dkv_kernel");
     return BDETR_OK;
 }

@@ -60,6 +60,9 @@ attention_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: dependents are released only after this CTA owns its TMEM columns (a dependent that grabbed TMEM first while
+    // blocked in griddepcontrol.wait could starve a late CTA of this grid); global data is touched below the wait.
+    pdl_sync();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -207,7 +210,7 @@ int launch_attention_fwd_umma(int B, int H, int Lq, int Lk, int d, const float *
     }
     const float scale_log2 = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
     dim3 grid(ceil_div(Lq, FA_BM), H, B);
-    attention_fwd_umma_kernel<<<grid, FA_THREADS, smem, s>>>(mq, mk, mv, H, Lq, Lk, o, lse, scale_log2, round_out);
+    launch_k(attention_fwd_umma_kernel, grid, FA_THREADS, smem, s, mq, mk, mv, H, Lq, Lk, o, lse, scale_log2, round_out);
     BDETR_CHECK_LAUNCH("attention_fwd_umma_kernel");
     return BDETR_OK;
 }

@@ -85,4 +85,30 @@ __device__ __forceinline__ float warp_max(float v)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// The step is ~800 short dependent kernels, so the drain -> launch -> ramp bubble between two kernels is a
+// large share of it.  Every kernel is launched with programmaticStreamSerialization: it signals
+// `launch_dependents` as soon as it starts, so the NEXT kernel's CTAs are scheduled onto free SMs and run their
+// prologue (barrier init, TMEM allocation, index math) while this one is still computing; the next kernel
+// then blocks in `griddepcontrol.wait` until this grid has completed and its writes are visible.  Every global
+// access of a kernel sits after its pdl_wait(), so the memory semantics are those of plain stream order.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // error picked up by BDETR_CHECK_LAUNCH
+}
+
 }  // namespace bdetr

@@ -22,6 +22,7 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(GTHREADS)
 gemm_simt_kernel(GemmArgs g)
 {
+    pdl_sync();
     __shared__ __align__(16) float As[2][GBK][GBM + GPAD];
     __shared__ __align__(16) float Bs[2][GBK][GBN + GPAD];
     const int tid = threadIdx.x;
@@ -112,6 +113,7 @@ gemm_simt_kernel(GemmArgs g)
 
 __global__ void zero_strided_kernel(int M, int N, float *C, int ldc)
 {
+    pdl_sync();
     const size_t total = (size_t)M * N;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
         C[(e / N) * ldc + (e % N)] = 0.0f;
@@ -144,14 +146,14 @@ int launch_gemm(int M, int N, int K, const float *A, int lda, bool TA, const flo
     splits = ceil_div(K, g.k_chunk);
     g.atomic_out = splits > 1;
     if (g.atomic_out && !beta) {
-        zero_strided_kernel<<<min(ceil_div(M * N, 256), 1184), 256, 0, s>>>(M, N, C, ldc);
+        launch_k(zero_strided_kernel, min(ceil_div(M * N, 256), 1184), 256, 0, s, M, N, C, ldc);
         BDETR_CHECK_LAUNCH("zero_strided_kernel");
     }
     dim3 grid(ceil_div(N, GBN), ceil_div(M, GBM), splits);
-    if (!TA && !TB) gemm_simt_kernel<false, false><<<grid, GTHREADS, 0, s>>>(g);
-    else if (!TA && TB) gemm_simt_kernel<false, true><<<grid, GTHREADS, 0, s>>>(g);
-    else if (TA && !TB) gemm_simt_kernel<true, false><<<grid, GTHREADS, 0, s>>>(g);
-    else gemm_simt_kernel<true, true><<<grid, GTHREADS, 0, s>>>(g);
+    if (!TA && !TB) launch_k(gemm_simt_kernel<false, false>, grid, GTHREADS, 0, s, g);
+    else if (!TA && TB) launch_k(gemm_simt_kernel<false, true>, grid, GTHREADS, 0, s, g);
+    else if (TA && !TB) launch_k(gemm_simt_kernel<true, false>, grid, GTHREADS, 0, s, g);
+    else launch_k(gemm_simt_kernel<true, true>, grid, GTHREADS, 0, s, g);
     BDETR_CHECK_LAUNCH("gemm_simt_kernel");
     return BDETR_OK;
 }
@@ -161,6 +163,7 @@ int launch_gemm(int M, int N, int K, const float *A, int lda, bool TA, const flo
 __global__ void __launch_bounds__(256)
 colsum_acc_kernel_v4(int M, int N, const float *__restrict__ src, float *__restrict__ dst, int rows_per_cta)
 {
+    pdl_sync();
     __shared__ float4 red[8][32];
     const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
     const int c = blockIdx.x * 128 + lane * 4;
@@ -181,6 +184,7 @@ colsum_acc_kernel_v4(int M, int N, const float *__restrict__ src, float *__restr
 __global__ void __launch_bounds__(256)
 colsum_acc_kernel(int M, int N, const float *__restrict__ src, float *__restrict__ dst, int rows_per_cta)
 {
+    pdl_sync();
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
     const int rbeg = blockIdx.y * rows_per_cta, rend = min(M, rbeg + rows_per_cta);
@@ -201,11 +205,11 @@ int launch_colsum_acc(int M, int N, const float *src, float *dst, cudaStream_t s
     if (N % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
         const int rows_per_cta = 64;
         dim3 grid(ceil_div(N, 128), ceil_div(M, rows_per_cta));
-        colsum_acc_kernel_v4<<<grid, 256, 0, s>>>(M, N, src, dst, rows_per_cta);
+        launch_k(colsum_acc_kernel_v4, grid, 256, 0, s, M, N, src, dst, rows_per_cta);
     } else {
         const int rows_per_cta = 256;
         dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_cta));
-        colsum_acc_kernel<<<grid, 256, 0, s>>>(M, N, src, dst, rows_per_cta);
+        launch_k(colsum_acc_kernel, grid, 256, 0, s, M, N, src, dst, rows_per_cta);
     }
     BDETR_CHECK_LAUNCH("colsum_acc_kernel");
     return BDETR_OK;

@@ -63,6 +63,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: dependents are released only after this CTA owns its TMEM columns (a dependent that grabbed TMEM first while
+    // blocked in griddepcontrol.wait could starve a late CTA of this grid); global data is touched below the wait.
+    pdl_sync();
     if (threadIdx.x == 0) UMMA_STAMP(1);
 
     if (warp == 0) {
@@ -254,7 +257,7 @@ static int launch_umma_inst(dim3 grid, const CUtensorMap &ma, const CUtensorMap 
         BDETR_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<BN, STAGES, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         optin = true;
     }
-    gemm_umma_kernel<BN, STAGES, A_MN, B_MN><<<grid, UM_THREADS, smem, s>>>(ma, mb, mc, ep);
+    launch_k(gemm_umma_kernel<BN, STAGES, A_MN, B_MN>, grid, UM_THREADS, smem, s, ma, mb, mc, ep);
     BDETR_CHECK_LAUNCH("gemm_umma_kernel");
     return BDETR_OK;
 }

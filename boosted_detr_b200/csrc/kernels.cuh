@@ -6,6 +6,20 @@ namespace bdetr {
 
 int current_mode();
 
+// Fork / join of independent kernel chains onto library-owned auxiliary streams.  The kernels of this workload
+// are short and at most ~100 CTAs wide, so independent ones (wgrad next to dgrad, the q/k/v projections) are
+// run side by side.  Every entry point joins what it forked before it returns, so callers still see plain
+// stream semantics on the stream they passed, and the fork/join is captured into CUDA graphs as parallel branches.
+struct Branches {
+    explicit Branches(cudaStream_t main_stream);
+    cudaStream_t fork(int i);       // aux stream i (0..2), ordered after everything enqueued on main so far
+    int join();                     // main waits for every aux stream forked since the last join
+    cudaStream_t main;
+    int base, used, rc;
+    bool on;
+};
+bool concurrency_enabled();
+
 // C[M,N] = (beta ? C : 0) + op(A)[M,K] @ op(B)[K,N] (+bias[n]) ; act 1 = relu ;
 // relu_mask != NULL: C[m,n] = 0 where relu_mask[m*ldc+n] <= 0 (backward of relu, applied last).
 // TA: A stored [K,M] (lda = M-stride of k rows); TB: B stored [N,K].

@@ -217,6 +217,7 @@ cost_matrix_kernel(int T, int Q, int C, int A,
                    const float *__restrict__ attr_pred, const float *__restrict__ box_pred,
                    float w_cat, float w_box, float w_attr, float *__restrict__ cost, CostSmemLayout L)
 {
+    pdl_sync();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *nlc = reinterpret_cast<float *>(smem_raw + L.off_nlc);
     float *dfs = reinterpret_cast<float *>(smem_raw + L.off_df);
@@ -363,6 +364,7 @@ cost_matrix_kernel(int T, int Q, int C, int A,
 __global__ void lsap_validate_kernel(int B, int T, int Q, const float *__restrict__ cost,
                                      const int32_t *__restrict__ num_objects, int32_t *__restrict__ status)
 {
+    pdl_sync();
     const size_t per = (size_t)T * Q, total = (size_t)B * per;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(e / per);
@@ -382,6 +384,7 @@ __global__ void __launch_bounds__(32)
 lsap_kernel(int T, int Q, const float *__restrict__ cost, const int32_t *__restrict__ num_objects,
             int32_t *__restrict__ col4row_out, int32_t *__restrict__ row4col_out, int32_t *__restrict__ status)
 {
+    pdl_sync();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, lane = threadIdx.x;
     const int N = max(T, Q);
@@ -499,6 +502,7 @@ __global__ void lsap_mask_kernel(int B, int T, int Q, const int32_t *__restrict_
                                  const int32_t *__restrict__ row4col, float *__restrict__ mask,
                                  float *__restrict__ assigned)
 {
+    pdl_sync();
     const size_t rows = (size_t)B * T;
     if (mask) {
         if ((Q & 3) == 0) {
@@ -563,6 +567,7 @@ matched_loss_fwd_kernel(int B, int T, int Q, int C, int A,
                         float w_cat, float w_box, float w_attr, float w_exist,
                         float *__restrict__ losses, float *__restrict__ iou)
 {
+    pdl_sync();
     __shared__ float red[ML_THREADS / 32];
     const int b = blockIdx.x, tid = threadIdx.x;
     const float total_n = total_objects(num_objects, B);
@@ -622,6 +627,7 @@ matched_loss_bwd_kernel(int B, int T, int Q, int C, int A,
                         float w_cat, float w_box, float w_attr, float w_exist, float gscale,
                         float *__restrict__ d_cat, float *__restrict__ d_attr, float *__restrict__ d_box)
 {
+    pdl_sync();
     const int e = blockIdx.x * ML_THREADS + threadIdx.x;
     if (e >= B * Q) return;
     const int b = e / Q;
@@ -698,10 +704,10 @@ extern "C" __attribute__((visibility("default"))) int bdetr_cost_matrix_fwd(int 
         optin[has_attr] = L.bytes;
     }
     if (has_attr) {
-        cost_matrix_kernel<true><<<grid, CM_THREADS, L.bytes, as_stream(stream)>>>(
+        launch_k(cost_matrix_kernel<true>, grid, CM_THREADS, L.bytes, as_stream(stream), 
             T, Q, C, A, cat_true, attr_true, box_true, cat_pred, attr_pred, box_pred, w_cat, w_box, w_attr, cost, L);
     } else {
-        cost_matrix_kernel<false><<<grid, CM_THREADS, L.bytes, as_stream(stream)>>>(
+        launch_k(cost_matrix_kernel<false>, grid, CM_THREADS, L.bytes, as_stream(stream), 
             T, Q, C, A, cat_true, attr_true, box_true, cat_pred, attr_pred, box_pred, w_cat, w_box, w_attr, cost, L);
     }
     BDETR_CHECK_LAUNCH("cost_matrix_kernel");
@@ -727,7 +733,7 @@ extern "C" __attribute__((visibility("default"))) int bdetr_lsap_assign(int B, i
     {
         const size_t total = (size_t)B * T * Q;
         const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-        lsap_validate_kernel<<<blocks, 256, 0, s>>>(B, T, Q, cost, num_objects, status);
+        launch_k(lsap_validate_kernel, blocks, 256, 0, s, B, T, Q, cost, num_objects, status);
         BDETR_CHECK_LAUNCH("lsap_validate_kernel");
     }
     static size_t lsap_optin = 0;
@@ -735,12 +741,12 @@ extern "C" __attribute__((visibility("default"))) int bdetr_lsap_assign(int B, i
         BDETR_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lsap_optin = smem;
     }
-    lsap_kernel<<<B, 32, smem, s>>>(T, Q, cost, num_objects, col4row, row4col, status);
+    launch_k(lsap_kernel, B, 32, smem, s, T, Q, cost, num_objects, col4row, row4col, status);
     BDETR_CHECK_LAUNCH("lsap_kernel");
     if (mask || assigned) {
         const size_t total = (size_t)B * T * Q / 4 + 1;
         const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-        lsap_mask_kernel<<<blocks, 256, 0, s>>>(B, T, Q, col4row, row4col, mask, assigned);
+        launch_k(lsap_mask_kernel, blocks, 256, 0, s, B, T, Q, col4row, row4col, mask, assigned);
         BDETR_CHECK_LAUNCH("lsap_mask_kernel");
     }
     return BDETR_OK;
@@ -759,7 +765,7 @@ extern "C" __attribute__((visibility("default"))) int bdetr_matched_loss_fwd(int
                   col4row && row4col && losses && iou, BDETR_E_NULL, "null pointer");
     cudaStream_t s = as_stream(stream);
     BDETR_CUDA(cudaMemsetAsync(iou, 0, sizeof(float) * Q, s));
-    matched_loss_fwd_kernel<<<B, ML_THREADS, 0, s>>>(B, T, Q, C, A, cat_true, attr_true, box_true, num_objects,
+    launch_k(matched_loss_fwd_kernel, B, ML_THREADS, 0, s, B, T, Q, C, A, cat_true, attr_true, box_true, num_objects,
                                                     cat_pred, attr_pred, box_pred, col4row, row4col,
                                                     w_cat, w_box, w_attr, w_exist, losses, iou);
     BDETR_CHECK_LAUNCH("matched_loss_fwd_kernel");
@@ -778,7 +784,7 @@ extern "C" __attribute__((visibility("default"))) int bdetr_matched_loss_bwd(int
     BDETR_REQUIRE(B > 0 && T > 0 && Q > 0 && C > 0 && A > 0, BDETR_E_BAD_SHAPE, "B,T,Q,C,A must be positive");
     BDETR_REQUIRE(cat_true && attr_true && box_true && num_objects && cat_pred && attr_pred && box_pred &&
                   row4col && d_cat_pred && d_attr_pred && d_box_pred, BDETR_E_NULL, "null pointer");
-    matched_loss_bwd_kernel<<<ceil_div(B * Q, ML_THREADS), ML_THREADS, 0, as_stream(stream)>>>(
+    launch_k(matched_loss_bwd_kernel, ceil_div(B * Q, ML_THREADS), ML_THREADS, 0, as_stream(stream), 
         B, T, Q, C, A, cat_true, attr_true, box_true, num_objects, cat_pred, attr_pred, box_pred, row4col,
         w_cat, w_box, w_attr, w_exist, gscale, d_cat_pred, d_attr_pred, d_box_pred);
     BDETR_CHECK_LAUNCH("matched_loss_bwd_kernel");

@@ -17,6 +17,7 @@ res_ln_fwd_kernel(int M, const float *__restrict__ resid, float *__restrict__ z,
                   const float *__restrict__ beta, float eps, float keep_scale, uint32_t thresh, uint32_t key,
                   float *__restrict__ out, float *__restrict__ mean_o, float *__restrict__ rstd_o, int round_out)
 {
+    pdl_sync();
     constexpr int D = NV * 128;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -65,6 +66,7 @@ res_ln_bwd_kernel(int M, const float *__restrict__ d_out, const float *__restric
                   uint32_t key, float *__restrict__ d_resid, int acc_resid, float *__restrict__ d_a,
                   float *__restrict__ g_gamma, float *__restrict__ g_beta, float *__restrict__ g_bias, int round_out)
 {
+    pdl_sync();
     constexpr int D = NV * 128;
     __shared__ float red_g[8][D + 4];
     __shared__ float red_b[8][D + 4];
@@ -157,9 +159,9 @@ int launch_res_ln_fwd(int M, int D, const float *resid, float *z, const float *g
     const uint32_t thresh = dropout_threshold(rate);
     const float ks = 1.0f / (1.0f - rate);
     const int grid = ceil_div(M, 8);
-    if (D == 128) res_ln_fwd_kernel<1><<<grid, 256, 0, s>>>(M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd, round_out);
-    else if (D == 256) res_ln_fwd_kernel<2><<<grid, 256, 0, s>>>(M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd, round_out);
-    else res_ln_fwd_kernel<4><<<grid, 256, 0, s>>>(M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd, round_out);
+    if (D == 128) launch_k(res_ln_fwd_kernel<1>, grid, 256, 0, s, M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd, round_out);
+    else if (D == 256) launch_k(res_ln_fwd_kernel<2>, grid, 256, 0, s, M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd, round_out);
+    else launch_k(res_ln_fwd_kernel<4>, grid, 256, 0, s, M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd, round_out);
     BDETR_CHECK_LAUNCH("res_ln_fwd_kernel");
     return BDETR_OK;
 }
@@ -172,9 +174,9 @@ int launch_res_ln_bwd(int M, int D, const float *d_out, const float *z, const fl
     const uint32_t thresh = dropout_threshold(rate);
     const float ks = 1.0f / (1.0f - rate);
     const int grid = min(ceil_div(M, 8), 296);
-    if (D == 128) res_ln_bwd_kernel<1><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
-    else if (D == 256) res_ln_bwd_kernel<2><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
-    else res_ln_bwd_kernel<4><<<grid, 256, 0, s>>>(M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
+    if (D == 128) launch_k(res_ln_bwd_kernel<1>, grid, 256, 0, s, M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
+    else if (D == 256) launch_k(res_ln_bwd_kernel<2>, grid, 256, 0, s, M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
+    else launch_k(res_ln_bwd_kernel<4>, grid, 256, 0, s, M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
     BDETR_CHECK_LAUNCH("res_ln_bwd_kernel");
     return BDETR_OK;
 }
@@ -189,6 +191,7 @@ __device__ __forceinline__ float4 round4(float4 v, int on)
 }
 __global__ void add_rows_fwd_kernel(size_t n4, size_t ld4, const float4 *__restrict__ x, const float4 *__restrict__ pos, float4 *__restrict__ out, int round_out)
 {
+    pdl_sync();
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
         const float4 a = x[e], p = pos[e % ld4];
         out[e] = round4(make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w), round_out);
@@ -196,10 +199,12 @@ __global__ void add_rows_fwd_kernel(size_t n4, size_t ld4, const float4 *__restr
 }
 __global__ void round_tf32_kernel(size_t n, const float *__restrict__ src, float *__restrict__ dst)
 {
+    pdl_sync();
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) dst[e] = tf32_rn(src[e]);
 }
 __global__ void batch_sum_acc_kernel(int B, size_t ld4, const float4 *__restrict__ src, float4 *__restrict__ dst)
 {
+    pdl_sync();
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < ld4; e += (size_t)gridDim.x * blockDim.x) {
         float4 a = dst[e];
         for (int b = 0; b < B; ++b) { const float4 v = src[(size_t)b * ld4 + e]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
@@ -208,10 +213,12 @@ __global__ void batch_sum_acc_kernel(int B, size_t ld4, const float4 *__restrict
 }
 __global__ void tile_rows_kernel(size_t n4, size_t ld4, const float4 *__restrict__ src, float4 *__restrict__ dst, int round_out)
 {
+    pdl_sync();
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) dst[e] = round4(src[e % ld4], round_out);
 }
 __global__ void accumulate_kernel(size_t n, const float *__restrict__ x, float *__restrict__ y)
 {
+    pdl_sync();
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) y[e] += x[e];
 }
 
@@ -221,7 +228,7 @@ int launch_add_rows_fwd(int B, int L, int D, const float *x, const float *pos, f
 {
     BDETR_REQUIRE(B > 0 && L > 0 && D > 0 && D % 4 == 0, BDETR_E_BAD_SHAPE, "D must be a multiple of 4");
     const size_t ld4 = (size_t)L * D / 4, n4 = ld4 * B;
-    add_rows_fwd_kernel<<<ew_grid(n4), 256, 0, s>>>(n4, ld4, (const float4 *)x, (const float4 *)pos, (float4 *)out, round_out);
+    launch_k(add_rows_fwd_kernel, ew_grid(n4), 256, 0, s, n4, ld4, (const float4 *)x, (const float4 *)pos, (float4 *)out, round_out);
     BDETR_CHECK_LAUNCH("add_rows_fwd_kernel");
     return BDETR_OK;
 }
@@ -229,7 +236,7 @@ int launch_batch_sum_acc(int B, int L, int D, const float *src, float *dst, cuda
 {
     BDETR_REQUIRE(B > 0 && L > 0 && D > 0 && D % 4 == 0, BDETR_E_BAD_SHAPE, "D must be a multiple of 4");
     const size_t ld4 = (size_t)L * D / 4;
-    batch_sum_acc_kernel<<<ew_grid(ld4), 256, 0, s>>>(B, ld4, (const float4 *)src, (float4 *)dst);
+    launch_k(batch_sum_acc_kernel, ew_grid(ld4), 256, 0, s, B, ld4, (const float4 *)src, (float4 *)dst);
     BDETR_CHECK_LAUNCH("batch_sum_acc_kernel");
     return BDETR_OK;
 }
@@ -237,21 +244,21 @@ int launch_tile_rows(int B, int L, int D, const float *src, float *dst, int roun
 {
     BDETR_REQUIRE(B > 0 && L > 0 && D > 0 && D % 4 == 0, BDETR_E_BAD_SHAPE, "D must be a multiple of 4");
     const size_t ld4 = (size_t)L * D / 4, n4 = ld4 * B;
-    tile_rows_kernel<<<ew_grid(n4), 256, 0, s>>>(n4, ld4, (const float4 *)src, (float4 *)dst, round_out);
+    launch_k(tile_rows_kernel, ew_grid(n4), 256, 0, s, n4, ld4, (const float4 *)src, (float4 *)dst, round_out);
     BDETR_CHECK_LAUNCH("tile_rows_kernel");
     return BDETR_OK;
 }
 int launch_round_tf32(size_t n, const float *src, float *dst, cudaStream_t s)
 {
     BDETR_REQUIRE(n > 0 && src && dst, BDETR_E_BAD_SHAPE, "bad round arguments");
-    round_tf32_kernel<<<ew_grid(n), 256, 0, s>>>(n, src, dst);
+    launch_k(round_tf32_kernel, ew_grid(n), 256, 0, s, n, src, dst);
     BDETR_CHECK_LAUNCH("round_tf32_kernel");
     return BDETR_OK;
 }
 int launch_accumulate(size_t n, const float *x, float *y, cudaStream_t s)
 {
     BDETR_REQUIRE(n > 0 && x && y, BDETR_E_BAD_SHAPE, "bad accumulate arguments");
-    accumulate_kernel<<<ew_grid(n), 256, 0, s>>>(n, x, y);
+    launch_k(accumulate_kernel, ew_grid(n), 256, 0, s, n, x, y);
     BDETR_CHECK_LAUNCH("accumulate_kernel");
     return BDETR_OK;
 }
@@ -278,6 +285,7 @@ constexpr int BN_ROWS = 128;     // rows per CTA: grid = (Dh/32, M/128) so the w
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(int M, int Dh, const float *__restrict__ h, float *__restrict__ acc)
 {
+    pdl_sync();
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
     const bool live = c < Dh;
@@ -295,6 +303,7 @@ bn_apply_kernel(int M, int Dh, const float *__restrict__ h, const float *__restr
                 float *__restrict__ moving_mean, float *__restrict__ moving_var, float eps, float momentum, int training,
                 const float *__restrict__ acc, float *__restrict__ hn, float *__restrict__ mean_o, float *__restrict__ rstd_o)
 {
+    pdl_sync();
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
     if (c >= Dh) return;
     float mean, var;
@@ -322,6 +331,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_stats_kernel(int M, int Dh, const float *__restrict__ h, const float *__restrict__ d_hn, const float *__restrict__ mean_i,
                     const float *__restrict__ rstd_i, float *__restrict__ acc)
 {
+    pdl_sync();
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
     const bool live = c < Dh;
@@ -344,6 +354,7 @@ bn_relu_bwd_apply_kernel(int M, int Dh, const float *__restrict__ h, const float
                          float *__restrict__ d_h, float *__restrict__ g_gamma, float *__restrict__ g_beta,
                          float *__restrict__ g_bias, int round_out)
 {
+    pdl_sync();
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
     if (c >= Dh) {                      // keep the block-wide reduction below convergent
@@ -379,10 +390,10 @@ int launch_bn_fwd(int M, int Dh, const float *h, const float *gamma, const float
     dim3 grid(ceil_div(Dh, 32), ceil_div(M, BN_ROWS));
     if (training) {
         BDETR_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 2 * Dh, s));
-        bn_stats_kernel<<<grid, 256, 0, s>>>(M, Dh, h, acc);
+        launch_k(bn_stats_kernel, grid, 256, 0, s, M, Dh, h, acc);
         BDETR_CHECK_LAUNCH("bn_stats_kernel");
     }
-    bn_apply_kernel<<<grid, 256, 0, s>>>(M, Dh, h, gamma, beta, moving_mean, moving_var, eps, momentum, training, acc, hn, mean, rstd);
+    launch_k(bn_apply_kernel, grid, 256, 0, s, M, Dh, h, gamma, beta, moving_mean, moving_var, eps, momentum, training, acc, hn, mean, rstd);
     BDETR_CHECK_LAUNCH("bn_apply_kernel");
     return BDETR_OK;
 }
@@ -393,9 +404,9 @@ int launch_bn_relu_bwd(int M, int Dh, const float *h, const float *d_hn, const f
     BDETR_REQUIRE(M > 0 && Dh > 0 && acc, BDETR_E_BAD_SHAPE, "bad BatchNorm arguments");
     dim3 grid(ceil_div(Dh, 32), ceil_div(M, BN_ROWS));
     BDETR_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 2 * Dh, s));
-    bn_bwd_stats_kernel<<<grid, 256, 0, s>>>(M, Dh, h, d_hn, mean, rstd, acc);
+    launch_k(bn_bwd_stats_kernel, grid, 256, 0, s, M, Dh, h, d_hn, mean, rstd, acc);
     BDETR_CHECK_LAUNCH("bn_bwd_stats_kernel");
-    bn_relu_bwd_apply_kernel<<<grid, 256, 0, s>>>(M, Dh, h, d_hn, gamma, mean, rstd, acc, d_h, g_gamma, g_beta, g_bias, round_out);
+    launch_k(bn_relu_bwd_apply_kernel, grid, 256, 0, s, M, Dh, h, d_hn, gamma, mean, rstd, acc, d_h, g_gamma, g_beta, g_bias, round_out);
     BDETR_CHECK_LAUNCH("bn_relu_bwd_apply_kernel");
     return BDETR_OK;
 }
@@ -409,6 +420,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 __global__ void __launch_bounds__(256)
 head_act_fwd_kernel(int M, int N, int kind, float mult, float *__restrict__ act, float *__restrict__ cum, int cum_init)
 {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -439,6 +451,7 @@ __global__ void __launch_bounds__(256)
 head_act_bwd_kernel(int M, int N, int kind, float mult, const float *__restrict__ act, const float *__restrict__ d_cum,
                     float *__restrict__ d_logits)
 {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -463,14 +476,14 @@ head_act_bwd_kernel(int M, int N, int kind, float mult, const float *__restrict_
 int launch_head_act_fwd(int M, int N, int kind, float mult, float *act, float *cum, int cum_init, cudaStream_t s)
 {
     BDETR_REQUIRE(M > 0 && N > 0 && kind >= 0 && kind <= 2, BDETR_E_BAD_SHAPE, "bad head activation arguments");
-    head_act_fwd_kernel<<<ceil_div(M, 8), 256, 0, s>>>(M, N, kind, mult, act, cum, cum_init);
+    launch_k(head_act_fwd_kernel, ceil_div(M, 8), 256, 0, s, M, N, kind, mult, act, cum, cum_init);
     BDETR_CHECK_LAUNCH("head_act_fwd_kernel");
     return BDETR_OK;
 }
 int launch_head_act_bwd(int M, int N, int kind, float mult, const float *act, const float *d_cum, float *d_logits, cudaStream_t s)
 {
     BDETR_REQUIRE(M > 0 && N > 0 && kind >= 0 && kind <= 2, BDETR_E_BAD_SHAPE, "bad head activation arguments");
-    head_act_bwd_kernel<<<ceil_div(M, 8), 256, 0, s>>>(M, N, kind, mult, act, d_cum, d_logits);
+    launch_k(head_act_bwd_kernel, ceil_div(M, 8), 256, 0, s, M, N, kind, mult, act, d_cum, d_logits);
     BDETR_CHECK_LAUNCH("head_act_bwd_kernel");
     return BDETR_OK;
 }

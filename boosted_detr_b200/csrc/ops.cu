@@ -15,14 +15,19 @@ static int linear_fwd(int M, int N, int K, const float *x, const float *W, const
 {
     return launch_gemm(M, N, K, x, K, false, W, N, false, b, act, nullptr, 0, rnd, y, N, s);
 }
-// gW += x^T dy ; gb += colsum(dy) ; dx (=|+=) dy W^T (optionally masked by relu_mask afterwards)
-static int linear_bwd(int M, int N, int K, const float *x, const float *W, const float *dy, float *gW, float *gb,
-                      float *dx, int acc_dx, const float *relu_mask, int rnd_dx, cudaStream_t s)
+// Backward of y = x W + b, as two independent halves (they run on different streams, see Branches):
+// weight half: gW += x^T dy ; gb += colsum(dy)
+static int linear_wgrad(int M, int N, int K, const float *x, const float *dy, float *gW, float *gb, cudaStream_t s)
 {
     if (gW) TRY(launch_gemm(K, N, M, x, K, true, dy, N, false, nullptr, 0, nullptr, 1, 0, gW, N, s));
     if (gb) TRY(launch_colsum_acc(M, N, dy, gb, s));
-    if (dx) TRY(launch_gemm(M, K, N, dy, N, false, W, N, true, nullptr, 0, relu_mask, acc_dx, rnd_dx, dx, K, s));
     return BDETR_OK;
+}
+// data half: dx (=|+=) dy W^T (optionally masked by relu_mask afterwards)
+static int linear_dgrad(int M, int N, int K, const float *W, const float *dy, float *dx, int acc_dx, const float *relu_mask,
+                        int rnd_dx, cudaStream_t s)
+{
+    return launch_gemm(M, K, N, dy, N, false, W, N, true, nullptr, 0, relu_mask, acc_dx, rnd_dx, dx, K, s);
 }
 
 API int bdetr_gemm(int M, int N, int K, const float *A, int transA, const float *Bm, int transB,
@@ -44,9 +49,12 @@ API int bdetr_attention_block_fwd(int B, int Lq, int Lk, int D, int H,
     const int Mq = B * Lq, Mk = B * Lk;
     const int rnd = tc_mode();
     // q/k/v feed the tcgen05 attention MMAs in tensor-core mode: store them tf32-rounded
+    Branches br(s);
+    cudaStream_t sk = br.fork(0), sv_s = br.fork(1);          // the three projections are independent
     TRY(linear_fwd(Mq, D, D, query, w->wq, w->bq, 0, sv->qp, rnd, s));
-    TRY(linear_fwd(Mk, D, D, key, w->wk, w->bk, 0, sv->kp, rnd, s));
-    TRY(linear_fwd(Mk, D, D, value, w->wv, w->bv, 0, sv->vp, rnd, s));
+    TRY(linear_fwd(Mk, D, D, key, w->wk, w->bk, 0, sv->kp, rnd, sk));
+    TRY(linear_fwd(Mk, D, D, value, w->wv, w->bv, 0, sv->vp, rnd, sv_s));
+    TRY(br.join());
     TRY(launch_attention_fwd(B, H, Lq, Lk, D / H, sv->qp, sv->kp, sv->vp, sv->o, sv->lse, rnd, s));
     // sv->o is [B,H,Lq,d]; read back as [B*Lq, D] with no permute (reference transformers.py:100)
     TRY(linear_fwd(Mq, D, D, sv->o, w->wo, w->bo, 0, sv->z, 0, s));
@@ -77,15 +85,22 @@ API int bdetr_attention_block_bwd(int B, int Lq, int Lk, int D, int H,
     const int rnd = tc_mode();
     TRY(launch_res_ln_bwd(Mq, D, d_out, sv->z, sv->mean, sv->rstd, w->ln_gamma, dropout_rate, dropout_key,
                           d_query, acc_flags & 1, sc->d_z, gw->ln_gamma, gw->ln_beta, gw->bo, rnd, s));
-    // output projection (its bias gradient was fused into the LayerNorm backward above)
-    // d_o feeds the tcgen05 attention backward MMAs in tensor-core mode: store it tf32-rounded
-    TRY(linear_bwd(Mq, D, D, sv->o, w->wo, sc->d_z, gw->wo, nullptr, sc->d_o, 0, nullptr, rnd, s));
+    // output projection (its bias gradient was fused into the LayerNorm backward above): the weight half runs
+    // beside the data path.  d_o feeds the tcgen05 attention backward MMAs in tensor-core mode: stored tf32-rounded
+    Branches br(s);
+    TRY(linear_wgrad(Mq, D, D, sv->o, sc->d_z, gw->wo, nullptr, br.fork(0)));
+    TRY(linear_dgrad(Mq, D, D, w->wo, sc->d_z, sc->d_o, 0, nullptr, rnd, s));
     TRY(launch_attention_bwd(B, H, Lq, Lk, D / H, sv->qp, sv->kp, sv->vp, sv->o, sv->lse, sc->d_o, sc->delta,
                              sc->d_qp, sc->d_kp, sc->d_vp, rnd, s));
-    TRY(linear_bwd(Mq, D, D, query, w->wq, sc->d_qp, gw->wq, gw->bq, d_query, 1, nullptr, 0, s));
-    TRY(linear_bwd(Mk, D, D, key, w->wk, sc->d_kp, gw->wk, gw->bk, d_key, (acc_flags >> 1) & 1, nullptr, 0, s));
-    TRY(linear_bwd(Mk, D, D, value, w->wv, sc->d_vp, gw->wv, gw->bv, d_value, (acc_flags >> 2) & 1, nullptr, 0, s));
-    return BDETR_OK;
+    // the three weight halves on three auxiliary streams; the data halves stay in order on the caller's stream
+    // because d_query / d_key / d_value may alias (q = k in the encoder, q = k = v in decoder self-attention)
+    TRY(linear_wgrad(Mq, D, D, query, sc->d_qp, gw->wq, gw->bq, br.fork(0)));
+    TRY(linear_wgrad(Mk, D, D, key, sc->d_kp, gw->wk, gw->bk, br.fork(1)));
+    TRY(linear_wgrad(Mk, D, D, value, sc->d_vp, gw->wv, gw->bv, br.fork(2)));
+    TRY(linear_dgrad(Mq, D, D, w->wq, sc->d_qp, d_query, 1, nullptr, 0, s));
+    TRY(linear_dgrad(Mk, D, D, w->wk, sc->d_kp, d_key, (acc_flags >> 1) & 1, nullptr, 0, s));
+    TRY(linear_dgrad(Mk, D, D, w->wv, sc->d_vp, d_value, (acc_flags >> 2) & 1, nullptr, 0, s));
+    return br.join();
 }
 
 API int bdetr_ffn_block_fwd(int M, int D, const float *x, const bdetr_ffn_params *w,
@@ -114,10 +129,13 @@ API int bdetr_ffn_block_bwd(int M, int D, const float *x, const bdetr_ffn_params
     const int rnd = tc_mode();
     TRY(launch_res_ln_bwd(M, D, d_out, sv->z, sv->mean, sv->rstd, w->ln_gamma, dropout_rate, dropout_key,
                           d_x, accumulate_dx, sc->d_z, gw->ln_gamma, gw->ln_beta, gw->b2, rnd, s));
-    // DenseLinear (bias gradient fused above), then ReLU mask on the way into DenseRelu
-    TRY(linear_bwd(M, D, D, sv->h, w->w2, sc->d_z, gw->w2, nullptr, sc->d_h, 0, sv->h, rnd, s));
-    TRY(linear_bwd(M, D, D, x, w->w1, sc->d_h, gw->w1, gw->b1, d_x, 1, nullptr, 0, s));
-    return BDETR_OK;
+    // DenseLinear (bias gradient fused above), then ReLU mask on the way into DenseRelu; weight halves run beside
+    Branches br(s);
+    TRY(linear_wgrad(M, D, D, sv->h, sc->d_z, gw->w2, nullptr, br.fork(0)));
+    TRY(linear_dgrad(M, D, D, w->w2, sc->d_z, sc->d_h, 0, sv->h, rnd, s));
+    TRY(linear_wgrad(M, D, D, x, sc->d_h, gw->w1, gw->b1, br.fork(1)));
+    TRY(linear_dgrad(M, D, D, w->w1, sc->d_h, d_x, 1, nullptr, 0, s));
+    return br.join();
 }
 
 API int bdetr_add_positional_fwd(int B, int L, int D, const float *x, const float *pos, float *out, void *stream)
@@ -176,9 +194,12 @@ API int bdetr_head_bwd(int M, int D, int Dh, int Nout, int kind, float mult,
     BDETR_REQUIRE(x && w && sv && d_cum && d_x && gw && sc && sc->d_logits && sc->d_hn && sc->d_h, BDETR_E_NULL, "null pointer");
     cudaStream_t s = as_stream(stream);
     TRY(launch_head_act_bwd(M, Nout, kind, mult, sv->act, d_cum, sc->d_logits, s));
-    TRY(linear_bwd(M, Nout, Dh, sv->hn, w->w2, sc->d_logits, gw->w2, gw->b2, sc->d_hn, 0, nullptr, 0, s));
+    Branches br(s);
+    TRY(linear_wgrad(M, Nout, Dh, sv->hn, sc->d_logits, gw->w2, gw->b2, br.fork(0)));
+    TRY(linear_dgrad(M, Nout, Dh, w->w2, sc->d_logits, sc->d_hn, 0, nullptr, 0, s));
     TRY(launch_bn_relu_bwd(M, Dh, sv->h, sc->d_hn, w->bn_gamma, sv->bn_mean, sv->bn_rstd, sv->bn_acc, sc->d_h, gw->bn_gamma,
                            gw->bn_beta, gw->b1, tc_mode(), s));
-    TRY(linear_bwd(M, Dh, D, x, w->w1, sc->d_h, gw->w1, nullptr, d_x, accumulate_dx, nullptr, 0, s));
-    return BDETR_OK;
+    TRY(linear_wgrad(M, Dh, D, x, sc->d_h, gw->w1, nullptr, br.fork(1)));
+    TRY(linear_dgrad(M, Dh, D, w->w1, sc->d_h, d_x, accumulate_dx, nullptr, 0, s));
+    return br.join();
 }

@@ -297,22 +297,36 @@ class DecoderPrep(Layer):
         # zeros initialiser, trainable (reference :427-431)
         self.add_weight("init_decoder_features", np.zeros((self.num_object_preds, self.decoder_dim), np.float32))
 
-    def forward(self, inputs, training=False):
+    def tile_queries(self, B, like=None):
+        """The learned queries tiled over the batch (:445-447).  Callable ahead of `forward` (the queries do not
+        depend on the image) so that the decoder self-attention can start early."""
+        if like is not None:
+            self.maybe_build([like])
+        q0 = self._weights["init_decoder_features"]
+        dec = empty(B, *q0.shape)
+        _lib.call("bdetr_tile_queries_fwd", B, q0.shape[0], q0.shape[1], ptr(q0), ptr(dec), stream_ptr())
+        return dec
+
+    def forward(self, inputs, training=False, dec=None):
         x4, pos = inputs
         x4 = f32(x4)
         self.maybe_build([x4])
         B, R, Cc, D = x4.shape
         enc_value = x4.view(B, R * Cc, D)
         enc_key = add_positional(enc_value, pos.reshape(-1, D)[: R * Cc])      # Add (:441)
-        q0 = self._weights["init_decoder_features"]
-        dec = empty(B, *q0.shape)
-        _lib.call("bdetr_tile_queries_fwd", B, q0.shape[0], q0.shape[1], ptr(q0), ptr(dec), stream_ptr())
+        if dec is None:
+            dec = self.tile_queries(B)
         return (enc_value, dec, enc_key, dec), {"shape": (B, R, Cc, D)}
 
-    def backward(self, ctx, d_enc_value, d_dec, d_enc_key, d_pos):
-        """Returns d_x4; accumulates into d_pos ([L,D]) and into the query parameter's gradient."""
-        B, R, Cc, D = ctx["shape"]
+    def backward_queries(self, d_dec):
+        """Gradient of the tiled queries -> the shared query parameter (sum over the batch)."""
         batch_sum_into(d_dec, self._grads["init_decoder_features"])
+
+    def backward(self, ctx, d_enc_value, d_dec, d_enc_key, d_pos):
+        """Returns d_x4; accumulates into d_pos ([L,D]) and (when d_dec is given) into the query parameter's gradient."""
+        B, R, Cc, D = ctx["shape"]
+        if d_dec is not None:
+            self.backward_queries(d_dec)
         batch_sum_into(d_enc_key, d_pos)
         accumulate(d_enc_key, d_enc_value)
         return d_enc_value.view(B, R, Cc, D)
@@ -330,17 +344,20 @@ class DecoderBlock_NoSelfAttention(Layer):
     def get_config(self):
         return {**super().get_config(), "num_attention_heads": self.num_attention_heads}
 
-    def forward(self, inputs, training=False, dropout_keys=(0, 0, 0)):
+    def forward(self, inputs, training=False, dropout_keys=(0, 0, 0), pre_self=None):
         enc_value, dec, enc_key, _ = inputs
         a, c1 = self.JointAttentionBlock.forward([dec, enc_key, enc_value], training, dropout_keys[1])
         y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[2])
         return y, {"joint": c1, "ffn": c2}
 
-    def backward(self, ctx, d_out):
+    def backward(self, ctx, d_out, defer_self=False):
         """Returns (d_enc_value, d_dec, d_enc_key)."""
         d_a = self.FeedForwardBlock.backward(ctx["ffn"], d_out)
         d_dec, d_key, d_val = self.JointAttentionBlock.backward(ctx["joint"], d_a)
         return d_val, d_dec, d_key
+
+    def backward_self(self, ctx, d_s):
+        return d_s                                # no self-attention in block 0: d_s already is the query gradient
 
 
 class DecoderBlock(Layer):
@@ -356,15 +373,24 @@ class DecoderBlock(Layer):
     def get_config(self):
         return {**super().get_config(), "num_attention_heads": self.num_attention_heads}
 
-    def forward(self, inputs, training=False, dropout_keys=(0, 0, 0)):
+    def forward(self, inputs, training=False, dropout_keys=(0, 0, 0), pre_self=None):
+        """pre_self: (output, ctx) of SelfAttentionBlock.forward([dec, dec, dec]) when the caller already ran it
+        (it depends on the queries only, so the model overlaps it with the encoder block)."""
         enc_value, dec, enc_key, _ = inputs
-        s, c0 = self.SelfAttentionBlock.forward([dec, dec, dec], training, dropout_keys[0])
+        s, c0 = pre_self if pre_self is not None else self.SelfAttentionBlock.forward([dec, dec, dec], training, dropout_keys[0])
         a, c1 = self.JointAttentionBlock.forward([s, enc_key, enc_value], training, dropout_keys[1])
         y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[2])
         return y, {"self": c0, "joint": c1, "ffn": c2}
 
-    def backward(self, ctx, d_out):
+    def backward(self, ctx, d_out, defer_self=False):
+        """Returns (d_enc_value, d_dec, d_enc_key); with defer_self the middle entry is the gradient of the
+        self-attention OUTPUT and the caller finishes with backward_self (on another stream)."""
         d_a = self.FeedForwardBlock.backward(ctx["ffn"], d_out)
         d_s, d_key, d_val = self.JointAttentionBlock.backward(ctx["joint"], d_a)
+        if defer_self:
+            return d_val, d_s, d_key
+        return d_val, self.backward_self(ctx, d_s), d_key
+
+    def backward_self(self, ctx, d_s):
         d_dec, _, _ = self.SelfAttentionBlock.backward(ctx["self"], d_s)     # q = k = v share one buffer
-        return d_val, d_dec, d_key
+        return d_dec

@@ -43,6 +43,16 @@ const char *bdetr_last_error(void);
 /* Process-wide compute mode used by the dense entry points. */
 int bdetr_set_mode(int mode);
 int bdetr_get_mode(void);
+/* Programmatic dependent launch (on by default): every kernel is launched with stream-serialisation relaxed and
+ * blocks in griddepcontrol.wait before its first global access, so its prologue overlaps the previous kernel's
+ * tail.  Semantics are unchanged (plain stream order); the switch exists for A/B timing. */
+int bdetr_set_pdl(int on);
+/* Intra-call concurrency (on by default): independent kernel chains inside one entry point (wgrad next to dgrad,
+ * the q/k/v projections) run on library-owned auxiliary streams, forked from and joined back into the caller's
+ * stream before the call returns; CUDA-graph capturable. */
+int bdetr_set_concurrency(int on);
+int bdetr_get_concurrency(void);
+int bdetr_get_pdl(void);
 /* Number of kernels launched by this library since the last reset (bench.py's gpu_launches). */
 long long bdetr_launch_count(void);
 void bdetr_reset_launch_count(void);
