@@ -193,32 +193,41 @@ class BoostedDETR:
         return self._side
 
     def _aux_streams(self):
-        """Three extra streams: two for the attribute / box heads (the three heads of a block are independent
-        chains of short kernels), one for the batch-invariant decoder self-attention."""
+        """Four extra streams: two for the attribute / box heads (the three heads of a block are independent
+        chains of short kernels), one for the batch-invariant decoder self-attention, one for the decoder chain."""
         if not _lib.load().bdetr_get_concurrency():
-            return [torch.cuda.current_stream()] * 3          # A/B switch: everything in order on one stream
+            return [torch.cuda.current_stream()] * 4          # A/B switch: everything in order on one stream
         if getattr(self, "_aux", None) is None:
-            self._aux = [torch.cuda.Stream() for _ in range(3)]
+            self._aux = [torch.cuda.Stream() for _ in range(4)]
         return self._aux
 
     # -- forward -------------------------------------------------------------------------------
     def forward(self, feats, y_true, training):
-        """The hot loop (reference :199-246).  Returns (y_pred, ctx)."""
+        """The hot loop (reference :199-246).  Returns (y_pred, ctx).
+
+        Scheduling.  Encoder block i+1 only needs encoder block i's output, while decoder i, the heads of block i
+        and its matching loss hang off that output as a side chain.  The kernels are short and at most ~100 CTAs
+        wide, so the step is latency-bound: the chains run on separate streams (captured as parallel branches
+        of the CUDA graph):
+            main     encoder 0 -> encoder 1 -> ... -> encoder N-1
+            dec      (after encoder i) DecoderPrep -> decoder i -> heads i        [cums chain, in block order]
+            aux0/1   attribute / box head of block i (forked from and joined into dec)
+            aux2     decoder self-attention of block i >= 1 (queries only: no dependency on the image at all)
+            side     cost matrix -> per-image assignment -> matched loss of block i (forked from dec)
+        and everything is joined into main before returning."""
         N = self.num_decoder_blocks
         use_dropout = training and self.dropout_seed is not None
         x = feats
-        # The matcher of block i (cost matrix -> per-image assignment -> matched loss) does not feed block i+1's
-        # forward and is latency-bound on a handful of warps, so it runs on a side stream underneath the next
-        # block's GEMMs / attention and is joined before the backward (also captured as a parallel graph branch).
         main = torch.cuda.current_stream()
         side = self._side_stream() if training else None
+        aux = self._aux_streams()
+        dec_s = aux[3]
         if self.tensor_core_mode():
             self.refresh_shadow()
             x = torch.empty_like(feats)                        # the block input feeds tcgen05 GEMMs: round it too
             _lib.call("bdetr_round_tf32", feats.numel(), ptr(feats), ptr(x), stream_ptr())
         cums = None
         blocks, loss_ctxs = [], []
-        aux = self._aux_streams()
         for i in range(N):
             keys = self._keys(i) if use_dropout else None
             enc = self.EncoderTransformerBlocks[i]
@@ -228,8 +237,6 @@ class BoostedDETR:
             for nm in ("SelfAttentionBlock", "JointAttentionBlock", "FeedForwardBlock"):
                 if hasattr(dec_l, nm):
                     getattr(dec_l, nm).rate = 0.1 if use_dropout else 0.0
-            # Decoder self-attention (blocks >= 1) only sees the learned queries, not the image: it runs on its own
-            # stream underneath the encoder block and is joined in front of the cross-attention.
             dkeys = keys["dec"] if keys else (0, 0, 0)
             pre_self, dec0 = None, None
             # (not on the very first call: layers build lazily in execution order, and the weight-initialisation
@@ -240,69 +247,88 @@ class BoostedDETR:
                     dec0 = self.DecoderPrep.tile_queries(x.shape[0], like=x)
                     pre_self = dec_l.SelfAttentionBlock.forward([dec0, dec0, dec0], training, dkeys[0])
             (x, pos), c_enc = enc.forward([x], training, keys["enc"] if keys else None)
-            prep_out, c_prep = self.DecoderPrep.forward([x, pos], training, dec=dec0)
-            if pre_self is not None:
-                main.wait_stream(aux[2])
-            dec, c_dec = dec_l.forward(list(prep_out), training, dkeys, pre_self=pre_self)
-            mult = 2.0 if i == 0 else 1.0                 # block 0 is counted twice (reference :222-229)
-            if cums is not None and training:
-                cums = [c.clone() for c in cums]          # each block's loss keeps its own running prediction
-            heads = (self.CategoryBlocks[i], self.AttributeBlocks[i], self.BoxBlocks[i])
-            c_heads, new_cums = [], []
-            for h, head in enumerate(heads):                  # three independent chains: one stream each
-                st = main if h == 0 else aux[h - 1]
-                if st is not main:
-                    st.wait_stream(main)
-                with torch.cuda.stream(st):
-                    _, c = head.forward([dec], training, cum=None if cums is None else cums[h], mult=mult)
-                c_heads.append(c)
-                new_cums.append(c["cum"])
-            main.wait_stream(aux[0])
-            main.wait_stream(aux[1])
-            cums = new_cums
-            blocks.append({"enc": c_enc, "prep": c_prep, "dec": c_dec, "heads": c_heads})
-            if training:
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    loss_ctxs.append(self.loss_fn.forward(y_true, cums))
+            dec_s.wait_stream(main)
+            with torch.cuda.stream(dec_s):
+                prep_out, c_prep = self.DecoderPrep.forward([x, pos], training, dec=dec0)
+                if pre_self is not None:
+                    dec_s.wait_stream(aux[2])
+                dec, c_dec = dec_l.forward(list(prep_out), training, dkeys, pre_self=pre_self)
+                mult = 2.0 if i == 0 else 1.0                 # block 0 is counted twice (reference :222-229)
+                if cums is not None and training:
+                    cums = [c.clone() for c in cums]          # each block's loss keeps its own running prediction
+                heads = (self.CategoryBlocks[i], self.AttributeBlocks[i], self.BoxBlocks[i])
+                c_heads, new_cums = [], []
+                for h, head in enumerate(heads):              # three independent chains: one stream each
+                    st = dec_s if h == 0 else aux[h - 1]
+                    if st is not dec_s:
+                        st.wait_stream(dec_s)
+                    with torch.cuda.stream(st):
+                        _, c = head.forward([dec], training, cum=None if cums is None else cums[h], mult=mult)
+                    c_heads.append(c)
+                    new_cums.append(c["cum"])
+                dec_s.wait_stream(aux[0])
+                dec_s.wait_stream(aux[1])
+                cums = new_cums
+                blocks.append({"enc": c_enc, "prep": c_prep, "dec": c_dec, "heads": c_heads})
+                if training:
+                    side.wait_stream(dec_s)
+                    with torch.cuda.stream(side):
+                        loss_ctxs.append(self.loss_fn.forward(y_true, cums))
+        main.wait_stream(dec_s)
+        main.wait_stream(aux[2])
         if training:
             main.wait_stream(side)
         return cums, {"blocks": blocks, "loss": loss_ctxs, "y_true": y_true}
 
     def backward(self, ctx, gscale=1.0):
-        """Gradient of gscale * sum_b sum_i total_b^(i) w.r.t. every trainable weight (accumulated)."""
+        """Gradient of gscale * sum_b sum_i total_b^(i) w.r.t. every trainable weight (accumulated).
+
+        Same scheduling idea as forward: the loss / heads / decoder backward of ALL blocks only depends on the
+        running prediction gradient, not on the encoder backward, so that chain runs ahead on the `dec` stream
+        (heads on aux0/1, decoder self-attention backward on aux2) and hands (d_enc_value, d_enc_key) of block i
+        to the encoder chain on the main stream through an event."""
         N = self.num_decoder_blocks
         first = ctx["loss"][0]
         B, T, Q, C, A = first["dims"]
         r_cat, r_attr, r_box = zeros(B, Q, C), zeros(B, Q, A), zeros(B, Q, 4)
-        d_x_next = None
         main = torch.cuda.current_stream()
         aux = self._aux_streams()
-        keep = []                                            # buffers used on the auxiliary streams stay alive until the final join
+        dec_s = aux[3]
+        keep = [r_cat, r_attr, r_box]            # buffers used on other streams stay alive until the final join
+        handoff = [None] * N
+        dec_s.wait_stream(main)
+        with torch.cuda.stream(dec_s):
+            for i in reversed(range(N)):
+                blk = ctx["blocks"][i]
+                self.loss_fn.backward(ctx["loss"][i], r_cat, r_attr, r_box, gscale)
+                # the three heads are independent: category on this stream, attribute / box beside it
+                aux[0].wait_stream(dec_s)
+                aux[1].wait_stream(dec_s)
+                d_dec = self.CategoryBlocks[i].backward(blk["heads"][0], r_cat)
+                with torch.cuda.stream(aux[0]):
+                    d_dec_a = self.AttributeBlocks[i].backward(blk["heads"][1], r_attr)
+                with torch.cuda.stream(aux[1]):
+                    d_dec_b = self.BoxBlocks[i].backward(blk["heads"][2], r_box)
+                dec_s.wait_stream(aux[0])
+                dec_s.wait_stream(aux[1])
+                accumulate(d_dec_a, d_dec)
+                accumulate(d_dec_b, d_dec)
+                # decoder: FFN + cross-attention here; the self-attention backward (queries only) and the
+                # query-parameter gradient go to aux2
+                d_ev, d_s, d_ek = self.DecoderBlocks[i].backward(blk["dec"], d_dec, defer_self=True)
+                aux[2].wait_stream(dec_s)
+                with torch.cuda.stream(aux[2]):
+                    d_q = self.DecoderBlocks[i].backward_self(blk["dec"], d_s)
+                    self.DecoderPrep.backward_queries(d_q)
+                ev = torch.cuda.Event()
+                ev.record(dec_s)
+                handoff[i] = (d_ev, d_ek, ev)
+                keep += [d_dec, d_dec_a, d_dec_b, d_s, d_q, d_ev, d_ek]
+        d_x_next = None
         for i in reversed(range(N)):
             blk = ctx["blocks"][i]
-            self.loss_fn.backward(ctx["loss"][i], r_cat, r_attr, r_box, gscale)
-            # the three heads are independent: category on the main stream, attribute / box beside it
-            aux[0].wait_stream(main)
-            aux[1].wait_stream(main)
-            d_dec = self.CategoryBlocks[i].backward(blk["heads"][0], r_cat)
-            with torch.cuda.stream(aux[0]):
-                d_dec_a = self.AttributeBlocks[i].backward(blk["heads"][1], r_attr)
-            with torch.cuda.stream(aux[1]):
-                d_dec_b = self.BoxBlocks[i].backward(blk["heads"][2], r_box)
-            main.wait_stream(aux[0])
-            main.wait_stream(aux[1])
-            accumulate(d_dec_a, d_dec)
-            accumulate(d_dec_b, d_dec)
-            keep += [d_dec_a, d_dec_b]
-            # decoder: FFN + cross-attention on the main stream; the self-attention backward (queries only) and the
-            # query-parameter gradient go to aux[2] underneath the encoder backward
-            d_ev, d_s, d_ek = self.DecoderBlocks[i].backward(blk["dec"], d_dec, defer_self=True)
-            aux[2].wait_stream(main)
-            with torch.cuda.stream(aux[2]):
-                d_q = self.DecoderBlocks[i].backward_self(blk["dec"], d_s)
-                self.DecoderPrep.backward_queries(d_q)
-            keep += [d_s, d_q]
+            d_ev, d_ek, ev = handoff[i]
+            main.wait_event(ev)
             if d_x_next is not None:
                 accumulate(d_x_next.reshape(d_ev.shape), d_ev)
             enc = self.EncoderTransformerBlocks[i]
@@ -310,6 +336,7 @@ class BoostedDETR:
             g_pos = enc._grads["positional_encoding"].view(L, D)
             d_x4 = self.DecoderPrep.backward(blk["prep"], d_ev, None, d_ek, g_pos)
             d_x_next = enc.backward(blk["enc"], d_x4)
+        main.wait_stream(dec_s)
         main.wait_stream(aux[2])
         return d_x_next
 
@@ -325,14 +352,40 @@ class BoostedDETR:
     __call__ = call
 
     def _collect_metrics(self, ctx):
+        """add_loss / add_metric bookkeeping (reference :250-260).  Runs on the matcher's side stream so that the
+        backward does not wait for it; `_join_metrics` orders the caller's stream after it."""
         B = ctx["loss"][0]["dims"][0]
-        tot = zeros(5, B)
-        for c in ctx["loss"]:
-            accumulate(c["losses"], tot)
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if _lib.load().bdetr_get_concurrency() else main
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            tot = zeros(5, B)
+            for c in ctx["loss"]:
+                accumulate(c["losses"], tot)
+            iou = ctx["loss"][-1]["iou"]
+            # one [6] vector of the Keras-style batch means and one status vector: a single small D2H each per step
+            self.metric_means = torch.cat([tot.mean(dim=1), iou.mean().reshape(1)])
+            self.status_all = torch.stack([c["status"] for c in ctx["loss"]]).reshape(-1)
         self.losses = [tot[0]]                                # add_loss(loss) (reference :250)
         self.metric_tensors = {"loss": tot[0], "Category_Loss": tot[1], "Attribute_Loss": tot[2], "Box_Loss": tot[3],
-                               "Existence_Loss": tot[4], "IOU": ctx["loss"][-1]["iou"].unsqueeze(0)}
+                               "Existence_Loss": tot[4], "IOU": iou.unsqueeze(0)}
         return self.metric_tensors
+
+    def _join_metrics(self):
+        if _lib.load().bdetr_get_concurrency():
+            torch.cuda.current_stream().wait_stream(self._side_stream())
+
+    def host_logs(self):
+        """Metric means + matcher status to the host: two small pinned copies, one synchronisation."""
+        if getattr(self, "_host_buf", None) is None or self._host_buf[1].numel() != self.status_all.numel():
+            self._host_buf = (torch.empty(6, dtype=torch.float32).pin_memory(),
+                              torch.empty(self.status_all.numel(), dtype=torch.int32).pin_memory())
+        hm, hs = self._host_buf
+        hm.copy_(self.metric_means, non_blocking=True)
+        hs.copy_(self.status_all, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        raise_for_status(hs)
+        return {k: float(hm[j]) for j, k in enumerate(self.metrics_names)}
 
     def compile(self, optimizer=None, **kwargs):
         self.optimizer = optimizer
@@ -349,6 +402,7 @@ class BoostedDETR:
         self.last_ctx_train, self.last_preds = ctx, y_pred
         m = self._collect_metrics(ctx)
         self.backward(ctx, gscale=1.0 / self.num_replicas)
+        self._join_metrics()
         if self.grad_allreduce is not None:
             self.grad_allreduce(self._flat[1])
         if self.optimizer is not None:
@@ -358,9 +412,7 @@ class BoostedDETR:
             self.dropout_seed = (self.dropout_seed + 1) & 0xFFFFFFFF
         if not return_host:
             return m
-        for c in ctx["loss"]:
-            raise_for_status(c["status"])
-        return {k: float(v.mean().item()) for k, v in m.items()}
+        return self.host_logs()
 
     def test_step(self, inputs):
         return self.train_step(inputs)          # reference :269-270 (quirk Q8: validation also trains)

@@ -25,12 +25,13 @@ int current_mode() { return g_mode.load(std::memory_order_relaxed); }
 // ---- auxiliary stream pool (per device) ---------------------------------------------------------------------
 static std::atomic<int> g_conc{1};
 bool concurrency_enabled() { return g_conc.load(std::memory_order_relaxed) != 0; }
-constexpr int AUX_STREAMS = 9, MAX_DEVICES = 16;
+constexpr int AUX_GROUPS = 8, AUX_PER_GROUP = 3, AUX_STREAMS = AUX_GROUPS * AUX_PER_GROUP, MAX_DEVICES = 16;
 struct AuxPool {
     bool ready = false;
     cudaStream_t st[AUX_STREAMS];
     cudaEvent_t fork_ev[AUX_STREAMS], join_ev[AUX_STREAMS];
-    int next = 0;
+    cudaStream_t owner[AUX_GROUPS];      // caller stream each group of three auxiliary streams is bound to
+    int owners = 0, next = 0;
 };
 static AuxPool g_pools[MAX_DEVICES];
 static std::mutex g_pool_mu;
@@ -57,9 +58,17 @@ Branches::Branches(cudaStream_t main_stream) : main(main_stream), base(0), used(
     if (!on) return;
     AuxPool *p = pool_for_current_device();
     if (!p) { on = false; return; }
+    // Each caller stream gets its own group of auxiliary streams, so entry points issued from different caller
+    // streams (the model runs encoder / decoder / head chains side by side) never queue behind each other.
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    base = p->next;                       // rotate so that entry points issued from different caller streams
-    p->next = (p->next + 3) % AUX_STREAMS;   // do not queue behind each other on the same auxiliary stream
+    int g = -1;
+    for (int i = 0; i < p->owners; ++i) if (p->owner[i] == main_stream) { g = i; break; }
+    if (g < 0) {
+        if (p->owners < AUX_GROUPS) { g = p->owners++; }
+        else { g = p->next; p->next = (p->next + 1) % AUX_GROUPS; }       // more caller streams than groups: share
+        p->owner[g] = main_stream;
+    }
+    base = g * AUX_PER_GROUP;
 }
 
 cudaStream_t Branches::fork(int i)

@@ -41,8 +41,8 @@ class GraphedTrainStep:
         _, ctx = m.forward(s["features"], y_true, True)
         metrics = m._collect_metrics(ctx)
         m.backward(ctx, gscale=1.0 / m.num_replicas)
-        status = torch.stack([c["status"] for c in ctx["loss"]])
-        return metrics, status
+        m._join_metrics()
+        return metrics, m.status_all
 
     def load(self, inputs):
         """Host batch -> (pinned staging) -> static device buffers, async on the current stream."""
@@ -54,6 +54,9 @@ class GraphedTrainStep:
             if isinstance(x, torch.Tensor) and x.is_cuda:
                 if x.data_ptr() != dst.data_ptr():
                     dst.copy_(x.reshape(dst.shape), non_blocking=True)
+            elif isinstance(x, torch.Tensor) and x.is_pinned() and x.dtype == dst.dtype and x.is_contiguous():
+                dst.copy_(x.reshape(dst.shape), non_blocking=True)       # already in pinned host memory: no staging copy
+                m.h2d_bytes += x.numel() * x.element_size()
             else:
                 dst.copy_(m._pinned(k, x, dtype).reshape(dst.shape), non_blocking=True)
 
@@ -71,6 +74,4 @@ class GraphedTrainStep:
         self.replay()
         if not return_host:
             return self.metrics
-        out = {k: float(v.mean().item()) for k, v in self.metrics.items()}
-        raise_for_status(self.status.reshape(-1))
-        return out
+        return self.model.host_logs()
