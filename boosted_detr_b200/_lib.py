@@ -70,6 +70,7 @@ PROTOTYPES = {
     "bdetr_accumulate": (c_int, [c_size_t, P, P, P]),
     "bdetr_round_tf32": (c_int, [c_size_t, P, P, P]),
     "bdetr_debug_set_timeline": (c_int, [P]),
+    "bdetr_debug_force_attention_kernel": (c_int, [I]),
     "bdetr_head_fwd": (c_int, [I, I, I, I, I, I, F, P, POINTER(HeadParams), F, F, P, I, POINTER(HeadSaved), P]),
     "bdetr_head_bwd": (c_int, [I, I, I, I, I, F, P, POINTER(HeadParams), F, POINTER(HeadSaved), P, P, I,
                                POINTER(HeadParams), POINTER(HeadScratch), P]),

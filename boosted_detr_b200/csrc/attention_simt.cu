@@ -220,13 +220,20 @@ attention_bwd_dkv_kernel(int H, int Lq, int Lk, const float *__restrict__ qp, co
     }
 }
 
+int g_force_attention_kernel = 0;       // 0 auto, 1 one tile per CTA, 2 multi-stream (bdetr_debug_force_attention_kernel)
+
 int launch_attention_fwd(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
                          float *o, float *lse, int round_out, cudaStream_t s)
 {
     BDETR_REQUIRE(d == HD, BDETR_E_UNSUPPORTED, "head dim must be 32 (D/H)");
     BDETR_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0, BDETR_E_BAD_SHAPE, "bad attention shape");
-    if (current_mode() == BDETR_MODE_TF32 && attention_umma_eligible(B, H, Lq, Lk, d, qp, kp, vp))
+    if (current_mode() == BDETR_MODE_TF32 && attention_umma_eligible(B, H, Lq, Lk, d, qp, kp, vp)) {
+        // long sequences: three query tiles per CTA against a shared K/V ring (attention_umma_ms.cu)
+        const int force = g_force_attention_kernel;
+        if (force == 2 || (force == 0 && attention_umma_ms_eligible(B, H, Lq, Lk)))
+            return launch_attention_fwd_umma_ms(B, H, Lq, Lk, d, qp, kp, vp, o, lse, round_out, s);
         return launch_attention_fwd_umma(B, H, Lq, Lk, d, qp, kp, vp, o, lse, round_out, s);
+    }
     const float scale = 1.0f / sqrtf((float)d);
     dim3 grid(ceil_div(Lq, AT_THREADS), H, B);
     launch_k(attention_fwd_kernel, grid, AT_THREADS, 0, s, H, Lq, Lk, qp, kp, vp, o, lse, scale * LOG2E, round_out);

@@ -69,15 +69,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (threadIdx.x == 0) UMMA_STAMP(1);
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
+        // ===== TMA producer (warp-convergent loop, one elected lane issues) =====
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % UM_STAGES;
+            if (i >= UM_STAGES) mbar_wait(&empty[s], ((i / UM_STAGES) - 1) & 1);
+            const int k0 = (kb_beg + i) * UM_BK;
+            uint8_t *a_dst = smem_a + s * A_STAGE, *b_dst = smem_b + s * B_STAGE;
+            if (elect_one()) {
                 if (i == 1) UMMA_STAMP(2);
-                const int s = i % UM_STAGES;
-                if (i >= UM_STAGES) mbar_wait(&empty[s], ((i / UM_STAGES) - 1) & 1);
                 mbar_expect_tx(&full[s], A_STAGE + B_STAGE);
-                const int k0 = (kb_beg + i) * UM_BK;
-                uint8_t *a_dst = smem_a + s * A_STAGE, *b_dst = smem_b + s * B_STAGE;
                 if (!A_MN) {
                     tma_load_2d(a_dst, &map_a, k0, m0, &full[s]);                      // box {32 k, 128 rows}
                 } else {
@@ -91,17 +91,18 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_dst + j * 4096, &map_b, n0 + 32 * j, k0, &full[s]);      // box {32 n, 32 k}
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(UM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % UM_STAGES;
-                mbar_wait(&full[s], (i / UM_STAGES) & 1);
+        // ===== MMA issuer (warp-convergent loop, one elected lane issues) =====
+        constexpr uint32_t idesc = make_idesc_tf32(UM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % UM_STAGES;
+            mbar_wait(&full[s], (i / UM_STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_base = smem_u32(smem_a + s * A_STAGE), b_base = smem_u32(smem_b + s * B_STAGE);
+            if (elect_one()) {
                 if (i == 0) UMMA_STAMP(3);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_base = smem_u32(smem_a + s * A_STAGE), b_base = smem_u32(smem_b + s * B_STAGE);
 #pragma unroll
                 for (int j = 0; j < UM_BK / 8; ++j) {                                   // UMMA_K = 8 for tf32
                     // K-major: 8 rows x 128B atoms, 1024B apart (SBO); advance 32B per k-step inside the swizzled row.
@@ -112,9 +113,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     umma_tf32(tmem_base, a_desc, b_desc, idesc, (i | j) != 0);
                 }
                 umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
+                if (i == nkb - 1) {
+                    umma_commit(accum_full);       // accumulator complete
+                    UMMA_STAMP(4);
+                }
             }
-            umma_commit(accum_full);               // accumulator complete
-            UMMA_STAMP(4);
+            __syncwarp();
         }
     } else {
         // ===== epilogue: warp w owns TMEM lanes 32*(w%4)..  Each lane holds one output row; a 32x32 block goes to

@@ -43,6 +43,11 @@ int launch_attention_bwd(int B, int H, int Lq, int Lk, int d, const float *qp, c
                          const float *o, const float *lse, const float *d_o, float *delta,
                          float *d_qp, float *d_kp, float *d_vp, int round_out, cudaStream_t s);
 
+// multi-stream variant for long sequences (attention_umma_ms.cu)
+bool attention_umma_ms_eligible(int B, int H, int Lq, int Lk);
+int launch_attention_fwd_umma_ms(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
+                                 float *o, float *lse, int round_out, cudaStream_t s);
+extern int g_force_attention_kernel;
 // tcgen05 flash attention forward (attention_umma.cu)
 bool attention_umma_eligible(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp);
 int launch_attention_fwd_umma(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,

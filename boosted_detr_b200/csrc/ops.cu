@@ -157,6 +157,12 @@ API int bdetr_accumulate(size_t n, const float *x, float *y, void *stream)
 {
     return launch_accumulate(n, x, y, as_stream(stream));
 }
+API int bdetr_debug_force_attention_kernel(int which)
+{
+    BDETR_REQUIRE(which >= 0 && which <= 2, BDETR_E_UNSUPPORTED, "0 auto, 1 one tile per CTA, 2 multi-stream");
+    bdetr::g_force_attention_kernel = which;
+    return BDETR_OK;
+}
 namespace bdetr { extern long long *g_umma_timeline; }
 API int bdetr_debug_set_timeline(long long *device_buf8)
 {

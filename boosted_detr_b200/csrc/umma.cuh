@@ -10,6 +10,22 @@ constexpr uint32_t SPIN_LIMIT = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a CONVERGENT warp.  The TMA / MMA issuing warps run their loops warp-wide and only predicate the
+// issuing instruction itself with this: descriptors and addresses then stay warp-uniform values (uniform registers),
+// whereas code nested under `if (lane == 0)` is divergent and every tcgen05.mma / TMA operand goes through a
+// register -> uniform-register waterfall (~80 cycles per instruction, measured: the issue loop, not the tensor pipe,
+// was the bound).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -30,6 +46,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (!done && ++spins > SPIN_LIMIT) __trap();     // never hang the GPU: a protocol bug becomes an error
     }
+}
+// non-blocking phase test
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
 {
@@ -149,6 +176,59 @@ __device__ __forceinline__ void tmem_st32_u(uint32_t taddr, const uint32_t v[32]
           "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
           "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
+}
+// Blackwell 3-input max and packed 2 x fp32 arithmetic (FMNMX3 / FFMA2 / FADD2): halve the instruction count of the
+// softmax inner loops and let the row reductions be written as short trees instead of 32-deep serial chains.
+__device__ __forceinline__ float max3f(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b)
+{
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// maximum of 32 floats held as raw bits: a 4-level tree of 3-input maxima (16 instructions, depth 4)
+__device__ __forceinline__ float max32_tree(const uint32_t v[32])
+{
+    float a[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = max3f(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+    a[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    const float b0 = max3f(a[0], a[1], a[2]), b1 = max3f(a[3], a[4], a[5]), b2 = max3f(a[6], a[7], a[8]), b3 = fmaxf(a[9], a[10]);
+    return fmaxf(max3f(b0, b1, b2), b3);
+}
+
+// 8-column TMEM load / store (rare fix-up paths that must stay small in registers)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t r[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t r[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 // MUFU.EX2: one instruction, flushes tiny results to zero (what a masked / far-below-max score should give)
 __device__ __forceinline__ float ex2_approx(float x)

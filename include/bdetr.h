@@ -241,6 +241,9 @@ int bdetr_head_bwd(int M, int D, int Dh, int Nout, int kind, float mult,
  * buffer (entry, setup done, 2nd TMA issue, first stage landed, last MMA committed, accumulator ready,
  * epilogue done, teardown).  Pass NULL to switch it off. */
 int bdetr_debug_set_timeline(long long *device_buf8);
+/* Debug / test aid: which tcgen05 attention-forward kernel the tensor-core mode uses.  0 = automatic (multi-stream
+ * kernel for long sequences, one tile per CTA otherwise), 1 = always one tile per CTA, 2 = always multi-stream. */
+int bdetr_debug_force_attention_kernel(int which);
 
 /* Generic row-major GEMM used by the entry points above, exported for tests and benchmarks:
  * C[M,N] = (beta ? C : 0) + op(A)[M,K] @ op(B)[K,N] (+ bias[N]) (relu if act==1).

@@ -164,3 +164,52 @@ def test_attention_block_tf32(tc_mode, B, Lq, Lk, selfattn):
             if "KeyProjection/bias" not in n}
     print("   weight grads worst:", max(werr.items(), key=lambda kv: kv[1]))
     assert max(werr.values()) < 1e-2
+
+
+@pytest.mark.parametrize("B,Lq,Lk,qscale", [(2, 2100, 2100, 1.0), (1, 500, 1300, 1.0), (3, 129, 64, 1.0), (1, 4096, 4096, 1.0),
+                                             (2, 700, 2100, 12.0)])
+def test_attention_core_multistream(tc_mode, B, Lq, Lk, qscale):
+    """Long-sequence tcgen05 attention (three query tiles per CTA against a shared K/V ring, attention_umma_ms.cu):
+    forced on at sizes with ragged query blocks (fewer than three live streams), a ragged last key tile and a
+    single key tile, and with 12x larger queries (peaky scores: the softmax reference maximum is raised in the
+    middle of tiles, which exercises the in-TMEM rescale of already written probabilities), against an fp64 softmax of the same tf32-rounded inputs and against the one-tile-per-CTA
+    kernel.  Tolerance 1e-3 normalised max error (north_star's reduced-precision bar)."""
+    from boosted_detr_b200 import _lib
+    from boosted_detr_b200.device import ptr, stream_ptr
+    lib = _lib.load()
+    H, d = 8, 32
+    D = H * d
+    rng = np.random.default_rng(Lq + Lk)
+
+    def tf32(x):                                      # round to nearest tf32 like the producers do
+        u = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+        u = ((u + 0x1000) & 0xFFFFE000).astype(np.uint32)
+        return u.view(np.float32)
+
+    q, k, v = (tf32(rng.standard_normal((B, L, D))) for L in (Lq, Lk, Lk))
+    q = tf32(q * qscale)
+    dq, dk, dv = (torch.from_numpy(x).cuda() for x in (q, k, v))
+    outs = {}
+    try:
+        for which in (2, 1):
+            assert lib.bdetr_debug_force_attention_kernel(which) == 0
+            o = torch.full((B, H, Lq, d), float("nan"), device="cuda"); lse = torch.full((B, H, Lq), float("nan"), device="cuda")
+            _lib.call("bdetr_attention_core_fwd", B, H, Lq, Lk, d, ptr(dq), ptr(dk), ptr(dv), ptr(o), ptr(lse), stream_ptr())
+            torch.cuda.synchronize()
+            outs[which] = (o.cpu().numpy(), lse.cpu().numpy())
+    finally:
+        lib.bdetr_debug_force_attention_kernel(0)
+    qh = q.astype(np.float64).reshape(B, Lq, H, d).transpose(0, 2, 1, 3)
+    kh = k.astype(np.float64).reshape(B, Lk, H, d).transpose(0, 2, 1, 3)
+    vh = v.astype(np.float64).reshape(B, Lk, H, d).transpose(0, 2, 1, 3)
+    s = qh @ kh.transpose(0, 1, 3, 2) / np.sqrt(d)
+    mx = s.max(-1, keepdims=True)
+    p = np.exp(s - mx)
+    ref_o = (p / p.sum(-1, keepdims=True)) @ vh
+    ref_lse = (np.log(p.sum(-1)) + mx[..., 0]) / np.log(2.0)
+    for which, (o, lse) in outs.items():
+        e_o, e_l = nerr(o, ref_o), nerr(lse, ref_lse)
+        print(f"attention core kernel {which} B{B} Lq{Lq} Lk{Lk}: o {e_o:.2e} lse {e_l:.2e}")
+        assert np.isfinite(o).all() and np.isfinite(lse).all()
+        assert e_o < 1e-3 and e_l < 1e-4
+    assert nerr(outs[2][0], outs[1][0]) < 1e-3        # same products, different softmax reference maximum / schedule
