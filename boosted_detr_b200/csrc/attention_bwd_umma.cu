@@ -73,33 +73,39 @@ attention_bwd_dq_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __
     pdl_sync();
     constexpr uint32_t COL_S = 0, COL_DP = 64, COL_DQ = 128;
 
+    // warps 0 / 1 walk their loops warp-convergent and only the issuing instructions are predicated on one elected
+    // lane (see elect_one in umma.cuh): descriptors stay in uniform registers.
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(qdo_full, 2 * FB_BIG);
             tma_load_2d(smem_q, &map_q, h * FB_HD, b * Lq + q0, qdo_full);
             tma_load_2d(smem_do, &map_do, 0, (b * H + h) * Lq + q0, qdo_full);
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t & 1;
-                if (t >= 2) mbar_wait(&kv_empty[s], ((t >> 1) - 1) & 1);
-                uint8_t *st = stage0 + s * 3 * FB_SMALL;
+        }
+        __syncwarp();
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t & 1;
+            if (t >= 2) mbar_wait(&kv_empty[s], ((t >> 1) - 1) & 1);
+            uint8_t *st = stage0 + s * 3 * FB_SMALL;
+            const int krow = b * Lk + t * FB_T;
+            if (elect_one()) {
                 mbar_expect_tx(&kv_full[s], 3 * FB_SMALL);
-                const int krow = b * Lk + t * FB_T;
                 tma_load_2d(st, &map_k, h * FB_HD, krow, &kv_full[s]);
                 tma_load_2d(st + FB_SMALL, &map_v, h * FB_HD, krow, &kv_full[s]);
                 tma_load_2d(st + 2 * FB_SMALL, &map_k_mn, h * FB_HD, krow, &kv_full[s]);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_tf32(FB_ROWS, FB_T, 0, 0);
-            constexpr uint32_t idesc_q = make_idesc_tf32(FB_ROWS, FB_HD, 0, 1);
-            mbar_wait(qdo_full, 0);
-            const uint32_t q_base = smem_u32(smem_q), do_base = smem_u32(smem_do);
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t & 1;
-                mbar_wait(&kv_full[s], (t >> 1) & 1);
-                tc_fence_after();
-                const uint32_t k_base = smem_u32(stage0 + s * 3 * FB_SMALL), v_base = k_base + FB_SMALL, kmn_base = k_base + 2 * FB_SMALL;
+        constexpr uint32_t idesc_s = make_idesc_tf32(FB_ROWS, FB_T, 0, 0);
+        constexpr uint32_t idesc_q = make_idesc_tf32(FB_ROWS, FB_HD, 0, 1);
+        mbar_wait(qdo_full, 0);
+        const uint32_t q_base = smem_u32(smem_q), do_base = smem_u32(smem_do);
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t & 1;
+            mbar_wait(&kv_full[s], (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t k_base = smem_u32(stage0 + s * 3 * FB_SMALL), v_base = k_base + FB_SMALL, kmn_base = k_base + 2 * FB_SMALL;
+            if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < FB_HD / 8; ++j)
                     umma_tf32(tmem_base + COL_S, make_smem_desc(q_base + j * 32, 16, 1024, 2), make_smem_desc(k_base + j * 32, 16, 1024, 2), idesc_s, j != 0);
@@ -107,14 +113,18 @@ attention_bwd_dq_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __
                 for (int j = 0; j < FB_HD / 8; ++j)
                     umma_tf32(tmem_base + COL_DP, make_smem_desc(do_base + j * 32, 16, 1024, 2), make_smem_desc(v_base + j * 32, 16, 1024, 2), idesc_s, j != 0);
                 umma_commit(sd_full);
-                mbar_wait(ds_full, t & 1);
-                tc_fence_after();
+            }
+            __syncwarp();
+            mbar_wait(ds_full, t & 1);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < FB_T / 8; ++j)
                     umma_tf32_ts(tmem_base + COL_DQ, tmem_base + COL_S + j * 8, make_smem_desc(kmn_base + j * 1024, 4096, 512, 1), idesc_q, (t | j) != 0);
                 umma_commit(&kv_empty[s]);
+                if (t == ntiles - 1) umma_commit(dq_full);
             }
-            umma_commit(dq_full);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;
@@ -219,33 +229,37 @@ attention_bwd_dkv_umma_kernel(const __grid_constant__ CUtensorMap map_k, const _
     const int orow0 = (b * H + h) * Lq;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(kv_full, 2 * FB_BIG);
             tma_load_2d(smem_k, &map_k, h * FB_HD, b * Lk + k0, kv_full);
             tma_load_2d(smem_v, &map_v, h * FB_HD, b * Lk + k0, kv_full);
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t & 1;
-                if (t >= 2) mbar_wait(&q_empty[s], ((t >> 1) - 1) & 1);
-                uint8_t *st = stage0 + s * 4 * FB_SMALL;
+        }
+        __syncwarp();
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t & 1;
+            if (t >= 2) mbar_wait(&q_empty[s], ((t >> 1) - 1) & 1);
+            uint8_t *st = stage0 + s * 4 * FB_SMALL;
+            const int qrow = b * Lq + t * FB_T, gorow = orow0 + t * FB_T;
+            if (elect_one()) {
                 mbar_expect_tx(&q_full[s], 4 * FB_SMALL);
-                const int qrow = b * Lq + t * FB_T, gorow = orow0 + t * FB_T;
                 tma_load_2d(st, &map_q, h * FB_HD, qrow, &q_full[s]);
                 tma_load_2d(st + FB_SMALL, &map_do, 0, gorow, &q_full[s]);
                 tma_load_2d(st + 2 * FB_SMALL, &map_q_mn, h * FB_HD, qrow, &q_full[s]);
                 tma_load_2d(st + 3 * FB_SMALL, &map_do_mn, 0, gorow, &q_full[s]);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_tf32(FB_ROWS, FB_T, 0, 0);
-            constexpr uint32_t idesc_a = make_idesc_tf32(FB_ROWS, FB_HD, 0, 1);
-            mbar_wait(kv_full, 0);
-            const uint32_t k_base = smem_u32(smem_k), v_base = smem_u32(smem_v);
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t & 1;
-                mbar_wait(&q_full[s], (t >> 1) & 1);
-                tc_fence_after();
-                const uint32_t qsw = smem_u32(stage0 + s * 4 * FB_SMALL), dosw = qsw + FB_SMALL, qmn = qsw + 2 * FB_SMALL, domn = qsw + 3 * FB_SMALL;
+        constexpr uint32_t idesc_s = make_idesc_tf32(FB_ROWS, FB_T, 0, 0);
+        constexpr uint32_t idesc_a = make_idesc_tf32(FB_ROWS, FB_HD, 0, 1);
+        mbar_wait(kv_full, 0);
+        const uint32_t k_base = smem_u32(smem_k), v_base = smem_u32(smem_v);
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t & 1;
+            mbar_wait(&q_full[s], (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t qsw = smem_u32(stage0 + s * 4 * FB_SMALL), dosw = qsw + FB_SMALL, qmn = qsw + 2 * FB_SMALL, domn = qsw + 3 * FB_SMALL;
+            if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < FB_HD / 8; ++j)
                     umma_tf32(tmem_base + COL_S, make_smem_desc(k_base + j * 32, 16, 1024, 2), make_smem_desc(qsw + j * 32, 16, 1024, 2), idesc_s, j != 0);
@@ -253,8 +267,11 @@ attention_bwd_dkv_umma_kernel(const __grid_constant__ CUtensorMap map_k, const _
                 for (int j = 0; j < FB_HD / 8; ++j)
                     umma_tf32(tmem_base + COL_DP, make_smem_desc(v_base + j * 32, 16, 1024, 2), make_smem_desc(dosw + j * 32, 16, 1024, 2), idesc_s, j != 0);
                 umma_commit(sd_full);
-                mbar_wait(pd_full, t & 1);
-                tc_fence_after();
+            }
+            __syncwarp();
+            mbar_wait(pd_full, t & 1);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < FB_T / 8; ++j)
                     umma_tf32_ts(tmem_base + COL_DV, tmem_base + COL_S + j * 8, make_smem_desc(domn + j * 1024, 4096, 512, 1), idesc_a, (t | j) != 0);
@@ -262,8 +279,9 @@ attention_bwd_dkv_umma_kernel(const __grid_constant__ CUtensorMap map_k, const _
                 for (int j = 0; j < FB_T / 8; ++j)
                     umma_tf32_ts(tmem_base + COL_DK, tmem_base + COL_DP + j * 8, make_smem_desc(qmn + j * 1024, 4096, 512, 1), idesc_a, (t | j) != 0);
                 umma_commit(&q_empty[s]);
+                if (t == ntiles - 1) umma_commit(acc_full);
             }
-            umma_commit(acc_full);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;

@@ -64,45 +64,55 @@ attention_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     // blocked in griddepcontrol.wait could starve a late CTA of this grid); global data is touched below the wait.
     pdl_sync();
 
+    // warps 0 / 1 walk their loops warp-convergent; only the issuing instructions are predicated on one elected lane
+    // (see elect_one in umma.cuh): descriptors stay in uniform registers.
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(q_full, FA_TILE_BYTES);
             tma_load_2d(smem_q, &map_q, h * FA_HD, b * Lq + q0, q_full);
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % FA_STAGES;
-                if (t >= FA_STAGES) mbar_wait(&kv_empty[s], ((t / FA_STAGES) - 1) & 1);
+        }
+        __syncwarp();
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % FA_STAGES;
+            if (t >= FA_STAGES) mbar_wait(&kv_empty[s], ((t / FA_STAGES) - 1) & 1);
+            if (elect_one()) {
                 mbar_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
                 tma_load_2d(smem_k + s * FA_TILE_BYTES, &map_k, h * FA_HD, b * Lk + t * FA_KT, &kv_full[s]);
                 tma_load_2d(smem_v + s * FA_TILE_BYTES, &map_v, h * FA_HD, b * Lk + t * FA_KT, &kv_full[s]);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_tf32(FA_BM, FA_KT, 0, 0);      // both K-major
-            constexpr uint32_t idesc_o = make_idesc_tf32(FA_BM, FA_HD, 0, 1);      // A from TMEM, B (V) MN-major
-            mbar_wait(q_full, 0);
-            const uint32_t q_base = smem_u32(smem_q);
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % FA_STAGES;
-                mbar_wait(&kv_full[s], (t / FA_STAGES) & 1);
-                tc_fence_after();
-                const uint32_t k_base = smem_u32(smem_k + s * FA_TILE_BYTES), v_base = smem_u32(smem_v + s * FA_TILE_BYTES);
-                // S = Q Kt (contraction over d = 32 = 4 k-steps of 8).  Issued after PV(t-1), so it cannot overwrite
-                // P(t-1) before that MMA has consumed it (the tensor pipe executes in issue order).
+        constexpr uint32_t idesc_s = make_idesc_tf32(FA_BM, FA_KT, 0, 0);      // both K-major
+        constexpr uint32_t idesc_o = make_idesc_tf32(FA_BM, FA_HD, 0, 1);      // A from TMEM, B (V) MN-major
+        mbar_wait(q_full, 0);
+        const uint32_t q_base = smem_u32(smem_q);
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % FA_STAGES;
+            mbar_wait(&kv_full[s], (t / FA_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t k_base = smem_u32(smem_k + s * FA_TILE_BYTES), v_base = smem_u32(smem_v + s * FA_TILE_BYTES);
+            // S = Q Kt (contraction over d = 32 = 4 k-steps of 8).  Issued after PV(t-1), so it cannot overwrite
+            // P(t-1) before that MMA has consumed it (the tensor pipe executes in issue order).
+            if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < FA_HD / 8; ++j)
                     umma_tf32(tmem_base, make_smem_desc(q_base + j * 32, 16, 1024, 2), make_smem_desc(k_base + j * 32, 16, 1024, 2),
                               idesc_s, j != 0);
                 umma_commit(s_full);
-                // O_tile = P V (contraction over the 128 keys = 16 k-steps of 8 TMEM columns / 8 V rows)
-                mbar_wait(p_full, t & 1);
-                tc_fence_after();
+            }
+            __syncwarp();
+            // O_tile = P V (contraction over the 128 keys = 16 k-steps of 8 TMEM columns / 8 V rows)
+            mbar_wait(p_full, t & 1);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < FA_KT / 8; ++j)
                     umma_tf32_ts(tmem_base + FA_O_COL, tmem_base + j * 8, make_smem_desc(v_base + j * 1024, 4096, 512, 1), idesc_o, j != 0);
                 umma_commit(&kv_empty[s]);
                 umma_commit(o_full);
             }
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;
@@ -127,8 +137,7 @@ attention_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
                 tmem_ld32_wait(cur);
                 if (c + 1 < FA_KT / 32) tmem_ld32_issue(lane_addr + (c + 1) * 32, nxt);
                 if (full_tile) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
+                    mx = fmaxf(mx, max32_tree(cur));              // 3-input max tree (depth 4) instead of a 32-deep chain
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < valid) ? __uint_as_float(cur[i]) : -CUDART_INF_F);
@@ -144,15 +153,32 @@ attention_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
                 uint32_t *cur = (c & 1) ? rb : ra, *nxt = (c & 1) ? ra : rb;
                 tmem_ld32_wait(cur);
                 if (c + 1 < FA_KT / 32) tmem_ld32_issue(lane_addr + (c + 1) * 32, nxt);
+                // keep the 10 mantissa bits the tf32 MMA will read (one LOP on the ALU pipe; cvt.rna would compete with
+                // ex2 for the XU pipe) and sum exactly those weights, so numerator and denominator of the softmax use
+                // identical values and the truncation bias cancels.  Packed FFMA2 / FADD2 and four independent partial
+                // sums keep the dependency chains short.
+                if (!full_tile) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    // keep the 10 mantissa bits the tf32 MMA will read (one LOP on the ALU pipe; cvt.rna would
-                    // compete with ex2 for the XU pipe) and sum exactly those weights, so numerator and
-                    // denominator of the softmax use identical values and the truncation bias cancels.
-                    uint32_t pb = __float_as_uint(ex2_approx(fmaf(__uint_as_float(cur[i]), scale_log2, -m_new))) & 0xFFFFE000u;
-                    if (!full_tile && c * 32 + i >= valid) pb = 0u;
-                    cur[i] = pb;
-                    psum += __uint_as_float(pb);
+                    for (int i = 0; i < 32; ++i) if (c * 32 + i >= valid) cur[i] = 0xFF800000u;          // -inf -> exp2 = 0
+                }
+                const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nm2 = pack_f32x2(-m_new, -m_new);
+                uint64_t ps_a = pack_f32x2(0.0f, 0.0f), ps_b = ps_a;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    float x0, x1, x2, x3;
+                    unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sc2, nm2), x0, x1);
+                    unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])), sc2, nm2), x2, x3);
+                    cur[i] = __float_as_uint(ex2_approx(x0)) & 0xFFFFE000u;
+                    cur[i + 1] = __float_as_uint(ex2_approx(x1)) & 0xFFFFE000u;
+                    cur[i + 2] = __float_as_uint(ex2_approx(x2)) & 0xFFFFE000u;
+                    cur[i + 3] = __float_as_uint(ex2_approx(x3)) & 0xFFFFE000u;
+                    ps_a = add_f32x2(ps_a, pack_f32x2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])));
+                    ps_b = add_f32x2(ps_b, pack_f32x2(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])));
+                }
+                {
+                    float s0, s1;
+                    unpack_f32x2(add_f32x2(ps_a, ps_b), s0, s1);
+                    psum += s0 + s1;
                 }
                 tmem_st32_u(lane_addr + c * 32, cur);
             }
