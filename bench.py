@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("BDETR_MODE", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after the backward instead of per-block buckets under it")
     ap.add_argument("--no-conc", action="store_true", help="disable multi-stream concurrency inside the step (A/B timing)")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch (A/B timing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -258,7 +259,7 @@ def main():
     lib.bdetr_set_pdl(0 if args.no_pdl else 1)
     lib.bdetr_set_concurrency(0 if args.no_conc else 1)
     model = make_model(cfg)
-    DataParallel(model)
+    DataParallel(model, overlap=not args.no_overlap)
     batch = synth_batch(rank, B, C, A, cfg)
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
 
@@ -327,7 +328,7 @@ def main():
         # count by running one eager (non-graph) step
         dev_batch = {k: torch.from_numpy(v).cuda() for k, v in batch.items()}
         lib.bdetr_reset_launch_count()
-        model.grad_allreduce = None            # rank 0 only from here on: no collectives
+        model.grad_allreduce = model.grad_bucket_hook = None     # rank 0 only from here on: no collectives
         model.train_step(dev_batch, return_host=False)
         torch.cuda.synchronize()
         launches_per_step = lib.bdetr_launch_count()
@@ -345,7 +346,7 @@ def main():
             "e2e": {"value": B * world / e2e_sec, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_sec * 1e3},
             "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
-            "cuda_graph": not args.no_graph, "pdl": not args.no_pdl, "concurrent_streams": not args.no_conc, "loss": logs.get("loss") if isinstance(logs, dict) else None,
+            "cuda_graph": not args.no_graph, "pdl": not args.no_pdl, "allreduce": ("none" if world == 1 else "one call after backward" if args.no_overlap else "per-block buckets overlapped with backward, inside the CUDA graph"), "concurrent_streams": not args.no_conc, "loss": logs.get("loss") if isinstance(logs, dict) else None,
             "step_algorithmic_tflops": flops / sec_per_step / 1e12, "roofline": roof}
     if not args.no_cpu_baseline and world == 1:
         sec = cpu_reference_steps(cfg, B, C, A, 1, 1, cores)

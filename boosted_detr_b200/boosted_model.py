@@ -13,6 +13,8 @@ train_step / test_step (which, as in the reference :269-270, also trains), per-b
 """
 from __future__ import annotations
 
+import re
+
 import numpy as np
 import torch
 
@@ -72,7 +74,8 @@ class BoostedDETR:
         self.dropout_seed = None          # None: dropout off (parity runs); int: hash-mask dropout, rate .1
         self.step_count = 0
         self.num_replicas = 1
-        self.grad_allreduce = None        # set by parallel.DataParallel
+        self.grad_allreduce = None        # set by parallel.DataParallel (joins / performs the gradient all-reduce)
+        self.grad_bucket_hook = None      # set by parallel.DataParallel: hook(block, lo, hi, events) as soon as a block's gradients are final
         self._flat = None
         self.metrics_names = ["loss", "Category_Loss", "Attribute_Loss", "Box_Loss", "Existence_Loss", "IOU"]
 
@@ -98,13 +101,32 @@ class BoostedDETR:
         return self
 
     def _flatten(self):
-        """Moves trainable weights / gradients into two flat buffers (one memset, one all-reduce)."""
+        """Moves trainable weights / gradients into two flat buffers (one memset, one all-reduce).  The slots are laid
+        out in the order the backward finishes them -- boosted block N-1 first, block 0 (plus the shared query
+        parameter) last -- so each block is one contiguous bucket that data-parallel runs can all-reduce while the
+        backward of the earlier blocks is still running (`_buckets`: (block, first float, one-past-last float))."""
+        N = self.num_decoder_blocks
+
+        def block_of(name):
+            m = re.match(r"[A-Za-z]+_(\d+)/", name)
+            return int(m.group(1)) if m else 0                # DecoderPrep (shared queries): final only after block 0
+
         named = [(n, o, k) for n, o, k in self.named_weights() if k not in o._non_trainable]
+        named.sort(key=lambda nok: -block_of(nok[0]))         # stable: keeps the layer order inside a block
         self._index, off = {}, 0
+        self._buckets, cur, start = [], None, 0
         for n, o, k in named:
+            blk = block_of(n)
+            if cur is None:
+                cur = blk
+            if blk != cur:
+                self._buckets.append((cur, start, off))
+                cur, start = blk, off
             w = o._weights[k]
             self._index[n] = (off, w.numel(), tuple(w.shape))
             off += (w.numel() + 3) // 4 * 4               # keep every tensor 16-byte aligned
+        self._buckets.append((cur, start, off))
+        assert [b for b, _, _ in self._buckets] == list(range(N - 1, -1, -1)), self._buckets
         flat_w, flat_g, flat_tc = zeros(off), zeros(off), zeros(off)
         for n, o, k in named:
             o0, cnt, shp = self._index[n]
@@ -320,14 +342,16 @@ class BoostedDETR:
                 with torch.cuda.stream(aux[2]):
                     d_q = self.DecoderBlocks[i].backward_self(blk["dec"], d_s)
                     self.DecoderPrep.backward_queries(d_q)
+                    self_ev = torch.cuda.Event()
+                    self_ev.record(aux[2])
                 ev = torch.cuda.Event()
                 ev.record(dec_s)
-                handoff[i] = (d_ev, d_ek, ev)
+                handoff[i] = (d_ev, d_ek, ev, self_ev)
                 keep += [d_dec, d_dec_a, d_dec_b, d_s, d_q, d_ev, d_ek]
         d_x_next = None
         for i in reversed(range(N)):
             blk = ctx["blocks"][i]
-            d_ev, d_ek, ev = handoff[i]
+            d_ev, d_ek, ev, self_ev = handoff[i]
             main.wait_event(ev)
             if d_x_next is not None:
                 accumulate(d_x_next.reshape(d_ev.shape), d_ev)
@@ -336,6 +360,12 @@ class BoostedDETR:
             g_pos = enc._grads["positional_encoding"].view(L, D)
             d_x4 = self.DecoderPrep.backward(blk["prep"], d_ev, None, d_ek, g_pos)
             d_x_next = enc.backward(blk["enc"], d_x4)
+            if self.grad_bucket_hook is not None and self._flat is not None:
+                # every gradient of boosted block i is final once this stream (encoder i, and through the hand-off
+                # event decoder i / heads i) and the self-attention stream have passed this point: its bucket can be
+                # all-reduced underneath the backward of blocks i-1 .. 0
+                _, lo, hi = self._buckets[N - 1 - i]
+                self.grad_bucket_hook(i, lo, hi, [self_ev])
         main.wait_stream(dec_s)
         main.wait_stream(aux[2])
         return d_x_next

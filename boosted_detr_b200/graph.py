@@ -42,6 +42,8 @@ class GraphedTrainStep:
         metrics = m._collect_metrics(ctx)
         m.backward(ctx, gscale=1.0 / m.num_replicas)
         m._join_metrics()
+        if m.grad_bucket_hook is not None and m.grad_allreduce is not None:
+            m.grad_allreduce(m._flat[1])          # joins the bucketed all-reduces issued inside the backward (captured too)
         return metrics, m.status_all
 
     def load(self, inputs):
@@ -63,8 +65,8 @@ class GraphedTrainStep:
     def replay(self):
         self.graph.replay()
         m = self.model
-        if m.grad_allreduce is not None:
-            m.grad_allreduce(m._flat[1])
+        if m.grad_allreduce is not None and m.grad_bucket_hook is None:
+            m.grad_allreduce(m._flat[1])          # non-overlapped mode: one all-reduce after the graph
         if m.optimizer is not None:
             m.optimizer.apply(m)
         m.step_count += 1

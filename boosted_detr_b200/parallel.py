@@ -53,16 +53,49 @@ def broadcast_tensor(t: torch.Tensor, src: int = 0):
 
 class DataParallel:
     """Attaches the gradient all-reduce to a BoostedDETR: model.train_step then computes
-    sum over replicas of d(loss_replica / world)/d(theta)."""
+    sum over replicas of d(loss_replica / world)/d(theta).
 
-    def __init__(self, model, bucket_bytes=None):
+    overlap=True (default): the flat gradient buffer is laid out block by block in backward order
+    (BoostedDETR._flatten), and as soon as the backward has finished boosted block i its bucket (~5 MB) is
+    all-reduced on a communication stream underneath the backward of blocks i-1 .. 0; only the last bucket is
+    exposed.  The collectives are issued in the same order on every rank and are captured into the CUDA graph of
+    the step together with the kernels.  overlap=False: one all-reduce of the whole buffer after the backward."""
+
+    def __init__(self, model, overlap=True):
         self.model = model
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.overlap = overlap and self.world > 1
+        self.comm_stream = None
         model.num_replicas = self.world
         if self.world > 1:
-            model.grad_allreduce = self.allreduce
+            model.grad_allreduce = self.finish
+            if self.overlap:
+                model.grad_bucket_hook = self.reduce_bucket
         self.broadcast_weights()
 
+    def _comm(self):
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream()
+        return self.comm_stream
+
+    def reduce_bucket(self, block: int, lo: int, hi: int, events=()):
+        """All-reduce flat_grads[lo:hi] (boosted block `block`) on the communication stream, ordered after the
+        caller's stream and `events`."""
+        comm = self._comm()
+        comm.wait_stream(torch.cuda.current_stream())
+        for ev in events:
+            comm.wait_event(ev)
+        with torch.cuda.stream(comm):
+            allreduce_gradients(self.model._flat[1][lo:hi])
+
+    def finish(self, flat_grads: torch.Tensor):
+        """Called at the end of the backward: joins the bucketed all-reduces, or does the single one."""
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(self._comm())
+        else:
+            allreduce_gradients(flat_grads)
+
+    # kept for callers that drive the collective themselves
     def allreduce(self, flat_grads: torch.Tensor):
         allreduce_gradients(flat_grads)
 

@@ -271,3 +271,37 @@ def test_model_train_step_vs_oracle(N, B, rows, cols, dropout, dataset):
     wd = model.get_weights_dict()
     for k, ref in stats.items():
         assert nerr(wd[k], ref) < 1e-5, k
+
+
+def test_gradient_buckets_follow_backward_order():
+    """Data-parallel overlap: the flat gradient buffer is one contiguous bucket per boosted block, in the order the
+    backward finishes them, and the bucket hook fires once per block with exactly those ranges; at that point on the
+    caller's stream + the passed events the bucket already holds its final values."""
+    N = 3
+    model, w, inputs = _model_and_data(N=N, B=2, rows=4, cols=4, Q=8, T=4)
+    flat_g = model._flat[1]
+    assert [b for b, _, _ in model._buckets] == list(range(N - 1, -1, -1))
+    assert model._buckets[0][1] == 0 and model._buckets[-1][2] == flat_g.numel()
+    assert all(model._buckets[k][2] == model._buckets[k + 1][1] for k in range(N - 1))
+    for name, (off, cnt, _) in model._index.items():
+        blk = int(name.split("/")[0].rsplit("_", 1)[1]) if name.split("/")[0].rsplit("_", 1)[-1].isdigit() else 0
+        lo, hi = next((l, h) for b, l, h in model._buckets if b == blk)
+        assert lo <= off and off + cnt <= hi, name
+    calls, snaps = [], {}
+    side = torch.cuda.Stream()
+
+    def hook(block, lo, hi, events):
+        calls.append((block, lo, hi))
+        side.wait_stream(torch.cuda.current_stream())
+        for ev in events:
+            side.wait_event(ev)
+        with torch.cuda.stream(side):
+            snaps[block] = flat_g[lo:hi].clone()
+
+    model.grad_bucket_hook = hook
+    model.train_step(inputs)
+    torch.cuda.synchronize()
+    assert calls == [(b, lo, hi) for b, lo, hi in model._buckets]
+    for b, lo, hi in model._buckets:
+        assert torch.equal(snaps[b], flat_g[lo:hi]), f"bucket of block {b} was still being written when its hook fired"
+        assert float(snaps[b].abs().sum()) > 0
