@@ -40,6 +40,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t *empty = full + UM_STAGES;
     uint64_t *accum_full = empty + UM_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+    float *smem_bias = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~uintptr_t(15));   // BN floats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool dbg_on = ep.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -126,34 +127,44 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // store -- or TMA reduce-add for accumulate / split-K -- which also clips the M and N tails.  The pipeline
         // stages are free once the accumulator is complete, so the staging boxes reuse them. =====
         const int q = warp & 3;
+        // bias -> shared memory while the mainloop runs (a global load per chunk would sit on the critical path of the
+        // epilogue: measured +1.1 us per GEMM)
+        const bool add_bias = ep.bias && (!ep.atomic_out || blockIdx.z == 0);
+        if (add_bias) {
+            const int e = threadIdx.x - 64;                    // 0..127
+            if (e < BN) smem_bias[e] = (n0 + e < ep.N) ? ep.bias[n0 + e] : 0.0f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+        }
         if (nkb > 0) {
             mbar_wait(accum_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         if (warp == 2 && lane == 0) UMMA_STAMP(5);
         const int row = m0 + q * 32 + lane;
-        const bool add_bias = ep.bias && (!ep.atomic_out || blockIdx.z == 0);
-#pragma unroll 1
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t ra[32], rb[32];
+        if (nkb > 0) tmem_ld32_issue(lane_addr, ra);
+#pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
             const int c0 = c * 32;
+            uint32_t *cur = (c & 1) ? rb : ra, *nxt = (c & 1) ? ra : rb;
             float v[32];
-            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-            else {
+            if (nkb > 0) {
+                tmem_ld32_wait(cur);
+                if (c + 1 < BN / 32) tmem_ld32_issue(lane_addr + c0 + 32, nxt);     // next chunk in flight while this one is written out
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cur[i]);
+            } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.0f;
             }
             const int ncol = ep.N - (n0 + c0);                 // columns of this chunk inside the matrix
             if (ncol > 0) {
                 if (add_bias) {
-                    if (ncol >= 32) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4 *>(ep.bias + n0 + c0 + i);
-                            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) if (i < ncol) v[i] += ep.bias[n0 + c0 + i];
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(smem_bias + c0 + i);     // broadcast read
+                        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
                     }
                 }
                 if (ep.act == 1) {
@@ -182,16 +193,29 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4 *>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0 && m0 + q * 32 < ep.M) {
-                    if (ep.atomic_out || ep.beta) tma_reduce_add_2d(&map_c, box, n0 + c0, m0 + q * 32);
-                    else tma_store_2d(&map_c, box, n0 + c0, m0 + q * 32);
-                    tma_store_commit();
-                }
             }
         }
-        if (lane == 0) tma_store_wait_all();
+        // One generic->async proxy fence for all staged boxes of this warp (it costs a few hundred cycles: once, not per
+        // chunk), then the elected lane hands the boxes to the TMA engine.
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (m0 + q * 32 < ep.M) {
+            if (elect_one()) {
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c) {
+                    if (ep.N - (n0 + c * 32) > 0) {
+                        uint8_t *box = smem + (size_t)(c * 4 + q) * 4096;
+                        if (ep.atomic_out || ep.beta) tma_reduce_add_2d(&map_c, box, n0 + c * 32, m0 + q * 32);
+                        else tma_store_2d(&map_c, box, n0 + c * 32, m0 + q * 32);
+                    }
+                }
+                tma_store_commit();
+                // the staging boxes are not reused: it is enough that the TMA engine has READ them before the CTA exits
+                // (the global writes complete asynchronously and are ordered before grid completion)
+                tma_store_wait_read_all();
+            }
+            __syncwarp();
+        }
     }
     if (warp == 2 && lane == 0) UMMA_STAMP(6);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -239,7 +263,7 @@ bool encode_tensor_map_2d(CUtensorMap *map, const float *base, long long rows, i
 }
 
 template <int BN, int STAGES>
-static size_t umma_smem_bytes() { return (size_t)STAGES * (UM_BM * UM_BK * 4 + BN * UM_BK * 4) + (2 * STAGES + 1) * 8 + 64 + 1024; }
+static size_t umma_smem_bytes() { return (size_t)STAGES * (UM_BM * UM_BK * 4 + BN * UM_BK * 4) + (2 * STAGES + 1) * 8 + 64 + BN * 4 + 1024; }
 
 bool umma_gemm_eligible(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB, int ldc)
 {

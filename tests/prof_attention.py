@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from boosted_detr_b200 import _lib
 from boosted_detr_b200.device import ptr, stream_ptr
 lib = _lib.load(); lib.bdetr_set_mode(_lib.MODE_TF32)
-B, Lq, Lk, H, d = 4, 4096, 4096, 8, 32
+B, Lq, Lk, H, d = 1, 20020, 20020, 8, 32      # BASELINE config 5 sequence length, one image
 D = H * d
 q = torch.randn(B, Lq, D, device="cuda"); k = torch.randn(B, Lk, D, device="cuda"); v = torch.randn(B, Lk, D, device="cuda")
 o = torch.empty(B, H, Lq, d, device="cuda"); lse = torch.empty(B, H, Lq, device="cuda")
