@@ -51,6 +51,9 @@ PROTOTYPES = {
     "bdetr_launch_count": (c_longlong, []),
     "bdetr_reset_launch_count": (None, []),
     "bdetr_cost_matrix_fwd": (c_int, [I, I, I, I, I, P, P, P, P, P, P, F, F, F, P, P]),
+    "bdetr_cost_targets_bytes": (c_size_t, [I, I, I, I]),
+    "bdetr_cost_targets_prepare": (c_int, [I, I, I, I, P, P, P, P, P]),
+    "bdetr_cost_matrix_prepared": (c_int, [I, I, I, I, I, P, P, P, P, F, F, F, P, P]),
     "bdetr_lsap_assign": (c_int, [I, I, I, P, P, P, P, P, P, P, P]),
     "bdetr_lsap_smem_bytes": (c_size_t, [I, I]),
     "bdetr_matched_loss_fwd": (c_int, [I, I, I, I, I, P, P, P, P, P, P, P, P, P, F, F, F, F, P, P, P]),

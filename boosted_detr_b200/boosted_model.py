@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from .device import empty, f32, i32, ptr, require_cuda, stream_ptr, zeros
 from .layers import Layer, dropout_key
-from .losses_and_metrics import MatchingLoss, raise_for_status
+from .losses_and_metrics import MatchingLoss, PreparedTargets, raise_for_status
 from .prediction_heads import BoxPredictionHead, MultiClassPredictionHead, SingleClassPredictionHead
 from .transformers import (DecoderBlock, DecoderBlock_NoSelfAttention, DecoderPrep, ImageEncoderAttention, accumulate)
 
@@ -250,6 +250,11 @@ class BoostedDETR:
             _lib.call("bdetr_round_tf32", feats.numel(), ptr(feats), ptr(x), stream_ptr())
         cums = None
         blocks, loss_ctxs = [], []
+        prepared = None
+        if training:                                           # one target batch, N matchings: digest the targets once
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                prepared = PreparedTargets(y_true)
         for i in range(N):
             keys = self._keys(i) if use_dropout else None
             enc = self.EncoderTransformerBlocks[i]
@@ -295,7 +300,7 @@ class BoostedDETR:
                 if training:
                     side.wait_stream(dec_s)
                     with torch.cuda.stream(side):
-                        loss_ctxs.append(self.loss_fn.forward(y_true, cums))
+                        loss_ctxs.append(self.loss_fn.forward(y_true, cums, prepared))
         main.wait_stream(dec_s)
         main.wait_stream(aux[2])
         if training:

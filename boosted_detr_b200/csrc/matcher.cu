@@ -7,6 +7,7 @@
 // shared-memory staging, no tensor cores (DESIGN.md "matcher kernels").
 #include <math_constants.h>
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace bdetr {
 
@@ -133,71 +134,124 @@ __device__ __forceinline__ float focal0(float pc)
 }
 
 // ---------------------------------------------------------------------------------------------
-// K7: cost matrix.  CTA = (image b, tile of QT prediction columns); thread = one column, looping
-// over a quarter of the target rows, so each warp stores 128 contiguous bytes per row.
+// K7: cost matrix.  CTA = (image b, tile of 64 prediction columns), 8 warps.  A thread owns TWO columns (lane and
+// lane + 32) and walks the target rows of its warp (t = warp, warp + 8, ...), so
+//   * the per-row data (box, hoisted invariants, class slot, attribute bits) is one 64-byte shared-memory record read
+//     with four broadcast LDS.128 and shared by both columns,
+//   * all add / sub / mul / fma work runs as packed f32x2 instructions (FADD2 / FFMA2: one issue slot for both
+//     columns; every lane is IEEE round-to-nearest, so the bits equal the scalar op-by-op evaluation),
+//   * each warp stores two full 128-byte lines per row.
+// The kernel is issue-bound, not HBM-bound (~45 instructions per pair after packing against 12.7 bytes per pair), so
+// the design removes instructions: -log(clip(p)+1e-7)/C is evaluated only for the classes that occur in the image's
+// targets (compacted "slots"), the attribute term of small vocabularies (A <= 4) is a 2^A-entry table per column, and
+// divisions are the Newton fast path.
 // ---------------------------------------------------------------------------------------------
-// a / b for normal, non-zero b: reciprocal estimate refined by Newton steps with exact FMA residuals -- the fast
-// path every IEEE-division expansion takes, without its range checks and slow-path call (the operands here are
-// box areas / class counts).  Rounds like a true division except in vanishingly rare double-rounding cases.
-__device__ __forceinline__ float div_rn_fast(float a, float b)
+typedef uint64_t f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// Product rounded once and NEVER contracted with a following add: ptxas (12.9) fuses mul.rn.f32x2 + add.rn.f32x2 into
+// one FFMA2 even with --fmad=false, which would change the bits.  An FMA whose addend is a -0.0 pair that only exists
+// at run time (kernel argument `nz`) is the exact product and cannot be folded.
+#define MUL2(a, b) fma2((a), (b), nz)
+
+// a / b lane-wise, the same Newton sequence as the scalar fast path: b == 0 lanes return 0 (divide_no_nan)
+__device__ __forceinline__ f32x2 div2_no_nan(f32x2 a, f32x2 b, f32x2 nz)
+{
+    float b0, b1, r0, r1;
+    upk2(b, b0, b1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(b0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(b1));
+    const f32x2 one = pk2(1.0f, 1.0f), nb = sub2(nz, b);              // -0 - b == -b exactly
+    f32x2 r = pk2(r0, r1);
+    r = fma2(fma2(nb, r, one), r, r);
+    const f32x2 q = MUL2(a, r);
+    float q0, q1;
+    upk2(fma2(fma2(nb, q, a), r, q), q0, q1);
+    return pk2(b0 == 0.0f ? 0.0f : q0, b1 == 0.0f ? 0.0f : q1);
+}
+// a / c for a per-thread constant c != 0 with rc = refined reciprocal of c (hoisted)
+__device__ __forceinline__ float rcp_refined(float c)
 {
     float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-    r = fmaf(fmaf(-b, r, 1.0f), r, r);
-    const float q = __fmul_rn(a, r);
-    return fmaf(fmaf(-b, q, a), r, q);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(c));
+    return fmaf(fmaf(-c, r, 1.0f), r, r);
 }
-__device__ __forceinline__ float div_no_nan_fast(float a, float b) { return b == 0.0f ? 0.0f : div_rn_fast(a, b); }
+__device__ __forceinline__ float div_by_const(float a, float c, float rc)
+{
+    const float q = __fmul_rn(a, rc);
+    return fmaf(fmaf(-c, q, a), rc, q);
+}
+__device__ __forceinline__ f32x2 div2_by_const(f32x2 a, float c, float rc, f32x2 nz)
+{
+    const f32x2 R = pk2(rc, rc), NC = pk2(-c, -c);
+    const f32x2 q = MUL2(a, R);
+    return fma2(fma2(NC, q, a), R, q);
+}
 
-constexpr int CM_QT = 64;
-constexpr int CM_THREADS = 512;
-constexpr int CM_TB = 12;        // floats kept per target box: ymin,xmin,ymax,xmax | area, 10*ymin,10*xmin,10*ymax | 10*xmax, nan flag, pad
+constexpr int CM_QT = 64;          // prediction columns per CTA (two per lane)
+constexpr int CM_THREADS = 256;
+constexpr int CM_WARPS = CM_THREADS / 32;
+constexpr int CM_ROW = 16;         // floats per target-row record
+constexpr int CM_SMALL_A = 4;      // attribute vocabularies up to this size use the 2^A table
+constexpr int CM_TAB = 17;         // row stride of that table (odd: conflict-free for a warp-uniform mask)
+
+// Prepared targets of one image ("blob", built once per batch by cost_targets_kernel, read by every column tile of
+// every boosted block through one TMA bulk copy):
+//   header  4 x u32   [0] number of class slots (distinct classes that occur), [1] magic divisor ceil(2^32 / slots)
+//   rows    T x 16 floats: [0..3] ymin xmin ymax xmax | [4,5] area twice | [6..13] 10*ymin, 10*xmin, 10*ymax, 10*xmax,
+//           each twice (ready-made f32x2 operands) | [14] meta: bits 0..15 class slot + 1 (0 = row is not one-hot ->
+//           general path), bit 30 = row identical to the last row (padding), bit 31 = NaN box | [15] attribute bit word 0
+//   cls_of  slot -> class (i16), slot_of class -> slot (i16), cbits [T][CW], abits [T][AW]
+struct CostBlobLayout {
+    int CW, AW;
+    uint32_t off_rows, off_clsof, off_slotof, off_cbits, off_abits, bytes;      // every offset and the size are multiples of 16
+};
+__host__ __device__ inline uint32_t cm_align16(uint32_t v) { return (v + 15u) & ~15u; }
+__host__ __device__ inline CostBlobLayout cost_blob_layout(int T, int C, int A)
+{
+    CostBlobLayout L;
+    L.CW = (C + 31) / 32; L.AW = (A + 31) / 32;
+    uint32_t o = 16;
+    L.off_rows = o; o += (uint32_t)T * CM_ROW * 4u;
+    L.off_clsof = o; o = cm_align16(o + (uint32_t)C * 2u);
+    L.off_slotof = o; o = cm_align16(o + (uint32_t)C * 2u);
+    L.off_cbits = o; o = cm_align16(o + (uint32_t)T * L.CW * 4u);
+    L.off_abits = o; o = cm_align16(o + (uint32_t)T * L.AW * 4u);
+    L.bytes = o;
+    return L;
+}
 
 struct CostSmemLayout {
-    int Cs, As, CW, AW;
-    uint32_t magicC, magicA;      // e / C == __umulhi(e, magicC) for e < 2^20 (exact: magic = ceil(2^32 / C))
-    size_t off_nlc, off_df, off_s0, off_tbox, off_cstar, off_cbits, off_abits, bytes;
+    int Cs, As;
+    size_t off_bar, off_raw, off_blob, off_nlc, off_attr, off_s0, bytes;
 };
 
 static CostSmemLayout cost_smem_layout(int T, int C, int A, bool has_attr)
 {
     CostSmemLayout L;
-    L.Cs = C; L.As = A; L.CW = (C + 31) / 32; L.AW = (A + 31) / 32;      // flat copies: the gather stride C is at worst 2-way conflicted
-    L.magicC = (uint32_t)((0x100000000ull + C - 1) / C); L.magicA = (uint32_t)((0x100000000ull + A - 1) / A);
+    L.Cs = C | 1; L.As = A | 1;                                        // odd strides: column-strided gathers are conflict-free
+    const bool small_a = A <= CM_SMALL_A;
     size_t o = 0;
+    L.off_bar = o; o += 16;
+    L.off_raw = o; o += sizeof(float) * CM_QT * C;                     // TMA destination: the tile's class probabilities as they sit in HBM
+    o = (o + 15) & ~size_t(15);
+    L.off_blob = o; o += cost_blob_layout(T, C, A).bytes;              // TMA destination: the image's prepared targets
     L.off_nlc = o; o += sizeof(float) * CM_QT * L.Cs;
-    L.off_df = o; if (has_attr) o += sizeof(float) * CM_QT * L.As;
+    L.off_attr = o; if (has_attr) o += sizeof(float) * CM_QT * (small_a ? CM_TAB : L.As);
     L.off_s0 = o; o += sizeof(float) * CM_QT;
-    L.off_tbox = o; o += sizeof(float) * CM_TB * T;
-    L.off_cstar = o; o += sizeof(int) * T;
-    L.off_cbits = o; o += sizeof(uint32_t) * T * L.CW;
-    L.off_abits = o; if (has_attr) o += sizeof(uint32_t) * T * L.AW;
     L.bytes = o;
     return L;
 }
 
-// Box term with the per-box invariants (areas, 10x coordinates) hoisted; same unfused arithmetic as
-// box_pair_cost, so the bits are identical.  NaN inputs are handled by the caller (flag), which lets the
-// min/max use the plain NaN-suppressing instructions.
-__device__ __forceinline__ float box_pair_cost_pre(const float (&t)[CM_TB], const float (&p)[9])
-{
-    const float iy0 = fmaxf(t[0], p[0]), ix0 = fmaxf(t[1], p[1]);
-    const float iy1 = fminf(t[2], p[2]), ix1 = fminf(t[3], p[3]);
-    const float iw = fmaxf(0.0f, __fsub_rn(ix1, ix0)), ih = fmaxf(0.0f, __fsub_rn(iy1, iy0));
-    const float ai = __fmul_rn(iw, ih);
-    const float un = __fsub_rn(__fadd_rn(t[4], p[4]), ai);
-    const float iou = div_no_nan_fast(ai, un);
-    const float ey0 = fminf(t[0], p[0]), ex0 = fminf(t[1], p[1]);
-    const float ey1 = fmaxf(t[2], p[2]), ex1 = fmaxf(t[3], p[3]);
-    const float ew = fmaxf(0.0f, __fsub_rn(ex1, ex0)), eh = fmaxf(0.0f, __fsub_rn(ey1, ey0));
-    const float ae = __fmul_rn(ew, eh);
-    const float giou = __fsub_rn(iou, div_no_nan_fast(__fsub_rn(ae, un), ae));
-    const float d0 = __fsub_rn(t[5], p[5]), d1 = __fsub_rn(t[6], p[6]), d2 = __fsub_rn(t[7], p[7]), d3 = __fsub_rn(t[8], p[8]);
-    const float ss = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
-    const float l2 = __fmul_rn(ss, 0.25f);                      // == ss / 4 exactly
-    return __fadd_rn(__fmul_rn(2.0f, __fsub_rn(1.0f, giou)), __fmul_rn(5.0f, l2));
-}
-__device__ __forceinline__ void box_invariants(float x, float y, float w, float h, float out[CM_TB])
+struct PredBox2 {                  // two prediction columns: scalars for min / max, packed invariants for the rest
+    float y0a, x0a, y1a, x1a, y0b, x0b, y1b, x1b;
+    f32x2 area, ty0, tx0, ty1, tx1;
+};
+
+__device__ __forceinline__ void pred_invariants(float x, float y, float w, float h, float out[9], bool &isnan_)
 {
     const BoxTF b = coco_to_tf(x, y, w, h);
     out[0] = b.ymin; out[1] = b.xmin; out[2] = b.ymax; out[3] = b.xmax;
@@ -205,157 +259,355 @@ __device__ __forceinline__ void box_invariants(float x, float y, float w, float 
     out[4] = __fmul_rn(bw, bh);
     out[5] = __fmul_rn(10.0f, b.ymin); out[6] = __fmul_rn(10.0f, b.xmin);
     out[7] = __fmul_rn(10.0f, b.ymax); out[8] = __fmul_rn(10.0f, b.xmax);
-    out[9] = (x != x || y != y || w != w || h != h) ? 1.0f : 0.0f;
-    out[10] = 0.0f; out[11] = 0.0f;
+    isnan_ = (x != x || y != y || w != w || h != h);
 }
 
-template <bool HAS_ATTR>
+// Box term of both columns against one target row; op order is box_pair_cost's (NaN inputs are flagged by the caller,
+// which lets min / max be the plain NaN-suppressing instructions).
+__device__ __forceinline__ f32x2 box_pair_cost_x2(const float4 tb, const f32x2 t_area, const f32x2 t0, const f32x2 t1,
+                                                  const f32x2 t2, const f32x2 t3, const PredBox2 &p, const f32x2 nz)
+{
+    const f32x2 IX0 = pk2(fmaxf(tb.y, p.x0a), fmaxf(tb.y, p.x0b)), IY0 = pk2(fmaxf(tb.x, p.y0a), fmaxf(tb.x, p.y0b));
+    const f32x2 IX1 = pk2(fminf(tb.w, p.x1a), fminf(tb.w, p.x1b)), IY1 = pk2(fminf(tb.z, p.y1a), fminf(tb.z, p.y1b));
+    float wa, wb, ha, hb;
+    upk2(sub2(IX1, IX0), wa, wb); upk2(sub2(IY1, IY0), ha, hb);
+    const f32x2 AI = MUL2(pk2(fmaxf(0.0f, wa), fmaxf(0.0f, wb)), pk2(fmaxf(0.0f, ha), fmaxf(0.0f, hb)));
+    const f32x2 UN = sub2(add2(t_area, p.area), AI);
+    const f32x2 IOU = div2_no_nan(AI, UN, nz);
+    const f32x2 EX0 = pk2(fminf(tb.y, p.x0a), fminf(tb.y, p.x0b)), EY0 = pk2(fminf(tb.x, p.y0a), fminf(tb.x, p.y0b));
+    const f32x2 EX1 = pk2(fmaxf(tb.w, p.x1a), fmaxf(tb.w, p.x1b)), EY1 = pk2(fmaxf(tb.z, p.y1a), fmaxf(tb.z, p.y1b));
+    upk2(sub2(EX1, EX0), wa, wb); upk2(sub2(EY1, EY0), ha, hb);
+    const f32x2 AE = MUL2(pk2(fmaxf(0.0f, wa), fmaxf(0.0f, wb)), pk2(fmaxf(0.0f, ha), fmaxf(0.0f, hb)));
+    const f32x2 GIOU = sub2(IOU, div2_no_nan(sub2(AE, UN), AE, nz));
+    const f32x2 D0 = sub2(t0, p.ty0), D1 = sub2(t1, p.tx0), D2 = sub2(t2, p.ty1), D3 = sub2(t3, p.tx1);
+    const f32x2 SS = add2(add2(add2(MUL2(D0, D0), MUL2(D1, D1)), MUL2(D2, D2)), MUL2(D3, D3));
+    const f32x2 L2 = MUL2(SS, pk2(0.25f, 0.25f));                      // == ss / 4 exactly
+    return add2(MUL2(pk2(2.0f, 2.0f), sub2(pk2(1.0f, 1.0f), GIOU)), MUL2(pk2(5.0f, 5.0f), L2));
+}
+
+// 1-D bulk copy global -> shared through the TMA engine, completion on an mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr uint32_t CM_META_TAIL = 1u << 30, CM_META_NAN = 1u << 31, CM_META_SLOT = 0xffffu;
+
+// K7a: target side, one CTA per image.  The one-hot / multi-hot blocks are staged in shared memory by TMA, turned into
+// bit words by warp ballots (no atomics, no index arithmetic), and reduced to the blob described above.
 __global__ void __launch_bounds__(CM_THREADS)
-cost_matrix_kernel(int T, int Q, int C, int A,
-                   const float *__restrict__ cat_true, const float *__restrict__ attr_true,
-                   const float *__restrict__ box_true, const float *__restrict__ cat_pred,
-                   const float *__restrict__ attr_pred, const float *__restrict__ box_pred,
-                   float w_cat, float w_box, float w_attr, float *__restrict__ cost, CostSmemLayout L)
+cost_targets_kernel(int T, int C, int A, const float *__restrict__ cat_true, const float *__restrict__ attr_true,
+                    const float *__restrict__ box_true, unsigned char *__restrict__ blobs, CostBlobLayout BL)
 {
     pdl_sync();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *nlc = reinterpret_cast<float *>(smem_raw + L.off_nlc);
-    float *dfs = reinterpret_cast<float *>(smem_raw + L.off_df);
-    float *s0 = reinterpret_cast<float *>(smem_raw + L.off_s0);
-    float *tbox = reinterpret_cast<float *>(smem_raw + L.off_tbox);
-    int *cstar = reinterpret_cast<int *>(smem_raw + L.off_cstar);
-    uint32_t *cbits = reinterpret_cast<uint32_t *>(smem_raw + L.off_cbits);
-    uint32_t *abits = reinterpret_cast<uint32_t *>(smem_raw + L.off_abits);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *present = reinterpret_cast<uint32_t *>(smem_raw + 16);           // CW words (<= 1024 classes)
+    unsigned char *blob = smem_raw + 16 + 128;
+    float *st_c = reinterpret_cast<float *>(blob + BL.bytes);
+    float *st_a = st_c + (((size_t)T * C + 3) & ~size_t(3));
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(blob);
+    float *rows = reinterpret_cast<float *>(blob + BL.off_rows);
+    int16_t *cls_of = reinterpret_cast<int16_t *>(blob + BL.off_clsof);
+    int16_t *slot_of = reinterpret_cast<int16_t *>(blob + BL.off_slotof);
+    uint32_t *cbits = reinterpret_cast<uint32_t *>(blob + BL.off_cbits);
+    uint32_t *abits = reinterpret_cast<uint32_t *>(blob + BL.off_abits);
 
-    const int b = blockIdx.y, tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int Cs = L.Cs, As = L.As, CW = L.CW, AW = L.AW;
-
-    // ---- target side: flat, division-free scans (independent loads, unrolled by the compiler) ----
-    for (int e = tid; e < T * CW; e += CM_THREADS) cbits[e] = 0u;
-    if (HAS_ATTR) for (int e = tid; e < T * AW; e += CM_THREADS) abits[e] = 0u;
-    __syncthreads();
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int CW = BL.CW, AW = BL.AW;
     const float *ct = cat_true + (size_t)b * T * C;
-#pragma unroll 4
-    for (int e = tid; e < T * C; e += CM_THREADS) {
-        if (ct[e] != 0.0f) { const int t = __umulhi((uint32_t)e, L.magicC), c = e - t * C; atomicOr(&cbits[t * CW + (c >> 5)], 1u << (c & 31)); }
+    const float *atp = attr_true + (size_t)b * T * A;
+    const uint32_t cb = (uint32_t)(T * C) * 4u, ab = (uint32_t)(T * A) * 4u;
+    const bool tma_c = ((reinterpret_cast<uintptr_t>(ct) | cb) & 15) == 0, tma_a = ((reinterpret_cast<uintptr_t>(atp) | ab) & 15) == 0;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, (tma_c ? cb : 0u) + (tma_a ? ab : 0u));
+        if (tma_c) bulk_load_1d(st_c, ct, cb, bar);
+        if (tma_a) bulk_load_1d(st_a, atp, ab, bar);
     }
-    if (HAS_ATTR) {
-        const float *atp = attr_true + (size_t)b * T * A;
-#pragma unroll 4
-        for (int e = tid; e < T * A; e += CM_THREADS) {
-            if (atp[e] != 0.0f) { const int t = __umulhi((uint32_t)e, L.magicA), a = e - t * A; atomicOr(&abits[t * AW + (a >> 5)], 1u << (a & 31)); }
-        }
+    if (tid < CW) present[tid] = 0u;
+    if (!tma_c) {
+#pragma unroll 8
+        for (int e = tid; e < T * C; e += CM_THREADS) st_c[e] = ct[e];
+    }
+    if (!tma_a) {
+#pragma unroll 8
+        for (int e = tid; e < T * A; e += CM_THREADS) st_a[e] = atp[e];
     }
     for (int t = tid; t < T; t += CM_THREADS) {
         const float4 bx = reinterpret_cast<const float4 *>(box_true)[(size_t)b * T + t];
-        float inv[CM_TB];
-        box_invariants(bx.x, bx.y, bx.z, bx.w, inv);
-#pragma unroll
-        for (int k = 0; k < CM_TB; k += 4)
-            *reinterpret_cast<float4 *>(tbox + t * CM_TB + k) = make_float4(inv[k], inv[k + 1], inv[k + 2], inv[k + 3]);
+        float inv[9]; bool tn;
+        pred_invariants(bx.x, bx.y, bx.z, bx.w, inv, tn);
+        float4 *r4 = reinterpret_cast<float4 *>(rows + t * CM_ROW);
+        r4[0] = make_float4(inv[0], inv[1], inv[2], inv[3]);
+        r4[1] = make_float4(inv[4], inv[4], inv[5], inv[5]);
+        r4[2] = make_float4(inv[6], inv[6], inv[7], inv[7]);
+        r4[3] = make_float4(inv[8], inv[8], __uint_as_float(tn ? CM_META_NAN : 0u), 0.0f);
     }
-    const float fC = (float)C, fA = (float)A;
-    const bool small_attr = HAS_ATTR && A <= 8;                 // branch-free attribute sum for tiny vocabularies
+    __syncthreads();
+    mbar_wait(bar, 0);
 
-    // ---- column tiles of this image handled by this CTA ----
-    for (int q0 = blockIdx.x * CM_QT; q0 < Q; q0 += gridDim.x * CM_QT) {
-        const int nq = min(CM_QT, Q - q0);
-        __syncthreads();                                        // bit sets complete / previous tile's readers done
-        if (q0 == blockIdx.x * CM_QT) {                         // first tile: single class of one-hot rows
-            for (int t = tid; t < T; t += CM_THREADS) {
-                int nset = 0, first = -1;
-                for (int w = 0; w < CW; ++w) {
-                    const uint32_t bits = cbits[t * CW + w];
-                    if (bits && first < 0) first = (w << 5) + __ffs(bits) - 1;
-                    nset += __popc(bits);
-                }
-                cstar[t] = nset == 1 ? first : -1;
-            }
+    for (int t = warp; t < T; t += CM_WARPS) {
+        for (int k = 0; k < CW; ++k) {
+            const int c = (k << 5) + lane;
+            const uint32_t bits = __ballot_sync(0xffffffffu, c < C && st_c[t * C + c] != 0.0f);
+            if (lane == 0) { cbits[t * CW + k] = bits; if (bits) atomicOr(&present[k], bits); }
         }
-        // prediction side: flat elementwise transforms of the tile (contiguous in HBM)
-        const float *cp = cat_pred + ((size_t)b * Q + q0) * C;
-#pragma unroll 4
-        for (int e = tid; e < nq * C; e += CM_THREADS) nlc[e] = div_rn_fast(neg_log_clip(cp[e]), fC);
-        if (HAS_ATTR) {
-            const float *ap = attr_pred + ((size_t)b * Q + q0) * A;
-#pragma unroll 4
-            for (int e = tid; e < nq * A; e += CM_THREADS) {
-                const float pc = safe_clip(ap[e]);
-                dfs[e] = __fsub_rn(focal1(pc), focal0(pc));
+        for (int k = 0; k < AW; ++k) {
+            const int a = (k << 5) + lane;
+            const uint32_t bits = __ballot_sync(0xffffffffu, a < A && st_a[t * A + a] != 0.0f);
+            if (lane == 0) abits[t * AW + k] = bits;
+        }
+    }
+    __syncthreads();
+    // class -> slot (rank among the classes that occur in this image), slot -> class
+    for (int c = tid; c < C; c += CM_THREADS) {
+        const int w = c >> 5;
+        const uint32_t word = present[w];
+        int s = -1;
+        if ((word >> (c & 31)) & 1u) {
+            s = __popc(word & ((1u << (c & 31)) - 1u));
+            for (int k = 0; k < w; ++k) s += __popc(present[k]);
+            cls_of[s] = (int16_t)c;
+        }
+        slot_of[c] = (int16_t)s;
+    }
+    if (tid == 0) {
+        int n = 0;
+        for (int k = 0; k < CW; ++k) n += __popc(present[k]);
+        hdr[0] = (uint32_t)n;
+        hdr[1] = n > 0 ? (uint32_t)((0x100000000ull + n - 1) / n) : 0u;
+        hdr[2] = 0u; hdr[3] = 0u;
+    }
+    __syncthreads();
+    uint32_t meta_new[1];                                                // T <= CM_THREADS is not assumed: loop, one row per pass
+    for (int t0 = 0; t0 < T; t0 += CM_THREADS) {
+        const int t = t0 + tid;
+        if (t < T) {
+            int nset = 0, first = -1;
+            bool same = true;                                            // identical to the last row, bit for bit?
+            for (int w = 0; w < CW; ++w) {
+                const uint32_t bits = cbits[t * CW + w];
+                if (bits && first < 0) first = (w << 5) + __ffs(bits) - 1;
+                nset += __popc(bits);
+                same = same && bits == cbits[(T - 1) * CW + w];
             }
-            // row sums of the y = 0 focal term: one warp per column
-            for (int q = warp; q < nq; q += CM_THREADS / 32) {
+            for (int w = 0; w < AW; ++w) same = same && abits[t * AW + w] == abits[(T - 1) * AW + w];
+            const uint4 mine = *reinterpret_cast<const uint4 *>(rows + t * CM_ROW), last = *reinterpret_cast<const uint4 *>(rows + (T - 1) * CM_ROW);
+            same = same && mine.x == last.x && mine.y == last.y && mine.z == last.z && mine.w == last.w;
+            uint32_t meta = __float_as_uint(rows[t * CM_ROW + 14]);
+            same = same && meta == __float_as_uint(rows[(T - 1) * CM_ROW + 14]);   // NaN flags (nothing else is set yet)
+            if (nset == 1) meta |= (uint32_t)(slot_of[first] + 1);
+            if (same) meta |= CM_META_TAIL;
+            meta_new[0] = meta;
+        }
+        __syncthreads();                                                 // every comparison against the last row's old meta is done
+        if (t < T) {
+            rows[t * CM_ROW + 14] = __uint_as_float(meta_new[0]);
+            rows[t * CM_ROW + 15] = __uint_as_float(abits[t * AW]);
+        }
+        __syncthreads();
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(blobs + (size_t)b * BL.bytes);
+    for (uint32_t e = tid; e < BL.bytes / 16; e += CM_THREADS) dst[e] = reinterpret_cast<const uint4 *>(blob)[e];
+}
+
+// K7b: the pairs.  CTA = (image b, tile of 64 prediction columns).
+template <bool HAS_ATTR, bool SMALL_A>
+__global__ void __launch_bounds__(CM_THREADS)
+cost_matrix_kernel(int T, int Q, int C, int A, const unsigned char *__restrict__ blobs,
+                   const float *__restrict__ cat_pred, const float *__restrict__ attr_pred, const float *__restrict__ box_pred,
+                   float w_cat, float w_box, float w_attr, float *__restrict__ cost, CostSmemLayout L, CostBlobLayout BL, f32x2 nz)
+{
+    pdl_sync();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + L.off_bar);
+    float *raw = reinterpret_cast<float *>(smem_raw + L.off_raw);
+    unsigned char *blob = smem_raw + L.off_blob;
+    float *nlc = reinterpret_cast<float *>(smem_raw + L.off_nlc);
+    float *attr_s = reinterpret_cast<float *>(smem_raw + L.off_attr);        // 2^A table (SMALL_A) or F1-F0 per attribute
+    float *s0 = reinterpret_cast<float *>(smem_raw + L.off_s0);
+    const uint32_t *hdr = reinterpret_cast<const uint32_t *>(blob);
+    const float *rows = reinterpret_cast<const float *>(blob + BL.off_rows);
+    const int16_t *cls_of = reinterpret_cast<const int16_t *>(blob + BL.off_clsof);
+    const int16_t *slot_of = reinterpret_cast<const int16_t *>(blob + BL.off_slotof);
+    const uint32_t *cbits = reinterpret_cast<const uint32_t *>(blob + BL.off_cbits);
+    const uint32_t *abits = reinterpret_cast<const uint32_t *>(blob + BL.off_abits);
+
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int Cs = L.Cs, As = L.As, CW = BL.CW, AW = BL.AW;
+    const int q0 = blockIdx.x * CM_QT, nq = min(CM_QT, Q - q0);
+
+    // ---- phase 0: everything this CTA reads more than once moves HBM/L2 -> shared memory with two TMA bulk copies
+    // (prepared targets, the tile's class probabilities); per-thread operands are loaded into registers meanwhile ----
+    const float *cp = cat_pred + ((size_t)b * Q + q0) * C;
+    const uint32_t tile_bytes = (uint32_t)(nq * C) * 4u;
+    const bool use_tma = ((reinterpret_cast<uintptr_t>(cp) | tile_bytes) & 15) == 0;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, BL.bytes + (use_tma ? tile_bytes : 0u));
+        bulk_load_1d(blob, blobs + (size_t)b * BL.bytes, BL.bytes, bar);
+        if (use_tma) bulk_load_1d(raw, cp, tile_bytes, bar);
+    }
+    const int qa = lane, qb = lane + 32;
+    const bool va = qa < nq, vb = qb < nq;
+    const int qbl = vb ? qb : (va ? qa : 0);                             // column b clamped for loads, never stored
+    const float4 pa4 = reinterpret_cast<const float4 *>(box_pred)[(size_t)b * Q + q0 + (va ? qa : 0)];
+    const float4 pb4 = reinterpret_cast<const float4 *>(box_pred)[(size_t)b * Q + q0 + qbl];
+    float pattr[CM_SMALL_A];
+    if (HAS_ATTR && SMALL_A && tid < nq) {
+#pragma unroll
+        for (int a = 0; a < CM_SMALL_A; ++a) pattr[a] = a < A ? attr_pred[((size_t)b * Q + q0 + tid) * A + a] : 0.5f;
+    }
+    if (!use_tma) {                                                      // unaligned tile: plain coalesced copy
+#pragma unroll 8
+        for (int e = tid; e < nq * C; e += CM_THREADS) raw[e] = cp[e];
+    }
+    __syncthreads();                                                     // barrier initialised (and the plain copy complete)
+    mbar_wait(bar, 0);
+    const int ns = (int)hdr[0];
+    const uint32_t magicS = hdr[1];
+
+    // ---- phase 4: prediction side of this column tile: -log(clip(p) + 1e-7) / C for the classes that occur only ----
+    const float fC = (float)C, fA = (float)A;
+    const float rC = rcp_refined(fC), rA = rcp_refined(fA);
+#pragma unroll 4
+    for (int e = tid; e < nq * ns; e += CM_THREADS) {
+        const int q = __umulhi((uint32_t)e, magicS), s = e - q * ns;
+        nlc[q * Cs + s] = div_by_const(neg_log_clip(raw[q * C + cls_of[s]]), fC, rC);
+    }
+    if (HAS_ATTR) {
+        if (SMALL_A) {
+            // table[q][m] = w_attr * ((s0 + sum_{a in m} (F1 - F0)(p_a)) / A), summed in attribute order; one thread per column
+            if (tid < nq) {
+                float df[CM_SMALL_A], sa0 = 0.0f;
+#pragma unroll
+                for (int a = 0; a < CM_SMALL_A; ++a) if (a < A) {
+                    const float pc = safe_clip(pattr[a]);
+                    const float f0 = focal0(pc);
+                    df[a] = __fsub_rn(focal1(pc), f0);
+                    sa0 = __fadd_rn(sa0, f0);
+                }
+                for (int m = 0; m < (1 << A); ++m) {
+                    float sa = sa0;
+#pragma unroll
+                    for (int a = 0; a < CM_SMALL_A; ++a) if (a < A) sa = __fadd_rn(sa, (m >> a) & 1 ? df[a] : 0.0f);
+                    attr_s[tid * CM_TAB + m] = __fmul_rn(w_attr, div_by_const(sa, fA, rA));
+                }
+            }
+        } else {
+            // one warp per column: F1 - F0 per attribute and the row sum of F0 (lane-strided partial sums, shuffle tree)
+            const float *ap = attr_pred + ((size_t)b * Q + q0) * A;
+            for (int q = warp; q < nq; q += CM_WARPS) {
                 float sacc = 0.0f;
-                for (int a = lane; a < A; a += 32) sacc += focal0(safe_clip(ap[q * A + a]));
+#pragma unroll 4
+                for (int a = lane; a < A; a += 32) {
+                    const float pc = safe_clip(ap[q * A + a]);
+                    const float f0 = focal0(pc);
+                    attr_s[q * As + a] = __fsub_rn(focal1(pc), f0);
+                    sacc += f0;
+                }
                 sacc = warp_sum(sacc);
                 if (lane == 0) s0[q] = sacc;
             }
         }
-        __syncthreads();
+    }
+    __syncthreads();
 
-        const int qi = tid % CM_QT, tg = tid / CM_QT;
-        if (qi < nq) {
-            const int q = q0 + qi;
-            const float4 pb = reinterpret_cast<const float4 *>(box_pred)[(size_t)b * Q + q];
-            float pinv[CM_TB];
-            box_invariants(pb.x, pb.y, pb.z, pb.w, pinv);
-            float p9[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) p9[k] = pinv[k];
-            const bool pnan = pinv[9] != 0.0f;
-            const float *my_nl = nlc + qi * Cs;
-            const float *my_df = dfs + qi * As;
-            const float my_s0 = HAS_ATTR ? s0[qi] : 0.0f;
-            float dfr[8];
-            if (small_attr) {
-#pragma unroll
-                for (int a = 0; a < 8; ++a) dfr[a] = a < A ? my_df[a] : 0.0f;
-            }
-            float *out = cost + (size_t)b * T * Q + q;
+    // ---- phase 5: the pairs.  lane -> columns (lane, lane + 32), warp -> rows ----
+    if (!va) return;
+    PredBox2 p;
+    uint32_t nan_a, nan_b;                                               // 0 or the quiet-NaN bits, OR-ed into the result
+    {
+        float ia[9], ib[9];
+        bool na, nb_;
+        pred_invariants(pa4.x, pa4.y, pa4.z, pa4.w, ia, na);
+        pred_invariants(pb4.x, pb4.y, pb4.z, pb4.w, ib, nb_);
+        p.y0a = ia[0]; p.x0a = ia[1]; p.y1a = ia[2]; p.x1a = ia[3];
+        p.y0b = ib[0]; p.x0b = ib[1]; p.y1b = ib[2]; p.x1b = ib[3];
+        p.area = pk2(ia[4], ib[4]); p.ty0 = pk2(ia[5], ib[5]); p.tx0 = pk2(ia[6], ib[6]); p.ty1 = pk2(ia[7], ib[7]); p.tx1 = pk2(ia[8], ib[8]);
+        nan_a = na ? 0x7fc00000u : 0u; nan_b = nb_ ? 0x7fc00000u : 0u;
+    }
+    // word offsets of this thread's columns inside the staged tables
+    int nl_a = qa * Cs, nl_b = qbl * Cs;
+    int at_a = qa * (SMALL_A ? CM_TAB : As), at_b = qbl * (SMALL_A ? CM_TAB : As);
+    f32x2 S0 = (HAS_ATTR && !SMALL_A) ? pk2(s0[qa], s0[qbl]) : 0ull;
+    f32x2 WCAT = pk2(w_cat, w_cat), WBOX = pk2(w_box, w_box);
+    const f32x2 WATTR = pk2(w_attr, w_attr);
+    // Everything above is loop-invariant and cheap to recompute, so the compiler would rematerialise it (S2R, x != x,
+    // 10 * x, q * Cs ...) inside the row loop: ~40 extra instructions per iteration.  Pin the values in registers.
+#define CM_KEEP_F(x) asm volatile("" : "+f"(x))
+#define CM_KEEP_R(x) asm volatile("" : "+r"(x))
+#define CM_KEEP_L(x) asm volatile("" : "+l"(x))
+    CM_KEEP_F(p.y0a); CM_KEEP_F(p.x0a); CM_KEEP_F(p.y1a); CM_KEEP_F(p.x1a);
+    CM_KEEP_F(p.y0b); CM_KEEP_F(p.x0b); CM_KEEP_F(p.y1b); CM_KEEP_F(p.x1b);
+    CM_KEEP_L(p.area); CM_KEEP_L(p.ty0); CM_KEEP_L(p.tx0); CM_KEEP_L(p.ty1); CM_KEEP_L(p.tx1);
+    CM_KEEP_R(nan_a); CM_KEEP_R(nan_b); CM_KEEP_R(nl_a); CM_KEEP_R(nl_b); CM_KEEP_R(at_a); CM_KEEP_R(at_b);
+    CM_KEEP_L(S0); CM_KEEP_L(WCAT); CM_KEEP_L(WBOX);
 
-#pragma unroll 2
-            for (int t = tg; t < T; t += CM_THREADS / CM_QT) {
-                float cat;
-                const int cs = cstar[t];
-                if (cs >= 0) {
-                    cat = __fadd_rn(0.0f, my_nl[cs]);               // one-hot row: a single gather
-                } else {
-                    cat = 0.0f;
-                    for (int w = 0; w < CW; ++w) {
-                        uint32_t bits = cbits[t * CW + w];
-                        while (bits) { const int c = __ffs(bits) - 1; bits &= bits - 1; cat = __fadd_rn(cat, my_nl[(w << 5) + c]); }
-                    }
-                }
-                float tb[CM_TB];
-#pragma unroll
-                for (int k = 0; k < CM_TB; k += 4) {
-                    const float4 v4 = *reinterpret_cast<const float4 *>(tbox + t * CM_TB + k);
-                    tb[k] = v4.x; tb[k + 1] = v4.y; tb[k + 2] = v4.z; tb[k + 3] = v4.w;
-                }
-                float box = box_pair_cost_pre(tb, p9);
-                if (pnan || tb[9] != 0.0f) box = CUDART_NAN_F;      // tf.maximum / minimum propagate NaN
-                float v = __fadd_rn(__fmul_rn(w_cat, cat), __fmul_rn(w_box, box));
-                if (HAS_ATTR) {
-                    float sa = my_s0;
-                    if (small_attr) {
-                        const uint32_t bits = abits[t * AW];
-#pragma unroll
-                        for (int a = 0; a < 8; ++a) sa = __fadd_rn(sa, (bits >> a) & 1u ? dfr[a] : 0.0f);   // + 0.0f is exact
-                    } else {
-                        for (int w = 0; w < AW; ++w) {
-                            uint32_t bits = abits[t * AW + w];
-                            while (bits) { const int a = __ffs(bits) - 1; bits &= bits - 1; sa = __fadd_rn(sa, my_df[(w << 5) + a]); }
-                        }
-                    }
-                    v = __fadd_rn(v, __fmul_rn(w_attr, div_rn_fast(sa, fA)));
-                } else {
-                    v = __fadd_rn(v, 0.0f);
-                }
-                out[(size_t)t * Q] = v;
+    // cost of both columns against row t (bits of the two results, NaN propagation included)
+    auto pair_cost = [&](int t, const float4 *r4, uint32_t &o0, uint32_t &o1) {
+        const float4 tb = r4[0];
+        const ulonglong2 ra = reinterpret_cast<const ulonglong2 *>(r4)[1], rb = reinterpret_cast<const ulonglong2 *>(r4)[2];
+        const float4 rc = r4[3];
+        const uint32_t meta = __float_as_uint(rc.z), abw = __float_as_uint(rc.w);
+        const int slot1 = (int)(meta & CM_META_SLOT);
+        f32x2 CAT;
+        if (slot1 > 0) {                                                 // one-hot row: one gather per column
+            CAT = pk2(nlc[nl_a + slot1 - 1], nlc[nl_b + slot1 - 1]);
+        } else {                                                         // general row: sum over its classes, ascending
+            CAT = pk2(0.0f, 0.0f);
+            for (int w = 0; w < CW; ++w) {
+                uint32_t bits = cbits[t * CW + w];
+                while (bits) { const int s = slot_of[(w << 5) + __ffs(bits) - 1]; bits &= bits - 1; CAT = add2(CAT, pk2(nlc[nl_a + s], nlc[nl_b + s])); }
             }
         }
+        const f32x2 BOX = box_pair_cost_x2(tb, ra.x, ra.y, rb.x, rb.y, pk2(rc.x, rc.y), p, nz);
+        f32x2 V = add2(MUL2(WCAT, CAT), MUL2(WBOX, BOX));
+        if (HAS_ATTR) {
+            if (SMALL_A) {
+                V = add2(V, pk2(attr_s[at_a + abw], attr_s[at_b + abw]));
+            } else {
+                f32x2 SA = S0;
+                for (int w = 0; w < AW; ++w) {
+                    uint32_t bits = w == 0 ? abw : abits[t * AW + w];
+                    while (bits) { const int a = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; SA = add2(SA, pk2(attr_s[at_a + a], attr_s[at_b + a])); }
+                }
+                V = add2(V, MUL2(WATTR, div2_by_const(SA, fA, rA, nz)));
+            }
+        }
+        float v0, v1;
+        upk2(V, v0, v1);
+        const uint32_t tnan = (uint32_t)((int32_t)meta >> 31) & 0x7fc00000u;   // tf.maximum / minimum propagate NaN
+        o0 = __float_as_uint(v0) | tnan | nan_a;
+        o1 = __float_as_uint(v1) | tnan | nan_b;
+    };
+
+    const float4 *rows4 = reinterpret_cast<const float4 *>(rows);
+    const float4 *r4 = rows4 + warp * (CM_ROW / 4);
+    uint32_t *out = reinterpret_cast<uint32_t *>(cost) + (size_t)b * T * Q + (size_t)warp * Q + q0 + qa;
+    const size_t out_step = (size_t)CM_WARPS * Q;
+    bool have_tail = false;
+    uint32_t tail0 = 0u, tail1 = 0u;
+#pragma unroll 1
+    for (int t = warp; t < T; t += CM_WARPS, r4 += CM_WARPS * (CM_ROW / 4), out += out_step) {
+        uint32_t o0, o1;
+        if (__float_as_uint(r4[3].z) & CM_META_TAIL) {                   // warp-uniform: rows equal to the last row share its cost
+            if (!have_tail) { pair_cost(T - 1, rows4 + (T - 1) * (CM_ROW / 4), tail0, tail1); have_tail = true; }
+            o0 = tail0; o1 = tail1;
+        } else {
+            pair_cost(t, r4, o0, o1);
+        }
+        out[0] = o0;
+        if (vb) out[32] = o1;
     }
+#undef CM_KEEP_F
+#undef CM_KEEP_R
+#undef CM_KEEP_L
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -700,33 +952,93 @@ matched_loss_bwd_kernel(int B, int T, int Q, int C, int A,
 
 using namespace bdetr;
 
+extern "C" __attribute__((visibility("default"))) size_t bdetr_cost_targets_bytes(int B, int T, int C, int A)
+{
+    if (B <= 0 || T <= 0 || C <= 0 || A <= 0) return 0;
+    return (size_t)B * cost_blob_layout(T, C, A).bytes;
+}
+
+static size_t cost_targets_smem(int T, int C, int A, const CostBlobLayout &BL)
+{
+    return 16 + 128 + BL.bytes + sizeof(float) * ((((size_t)T * C + 3) & ~size_t(3)) + (((size_t)T * A + 3) & ~size_t(3)));
+}
+
+extern "C" __attribute__((visibility("default"))) int bdetr_cost_targets_prepare(int B, int T, int C, int A,
+                                     const float *cat_true, const float *attr_true, const float *box_true,
+                                     void *prepared, void *stream)
+{
+    BDETR_REQUIRE(B > 0 && T > 0 && C > 0 && A > 0, BDETR_E_BAD_SHAPE, "B,T,C,A must be positive");
+    BDETR_REQUIRE(cat_true && attr_true && box_true && prepared, BDETR_E_NULL, "null pointer");
+    BDETR_REQUIRE((reinterpret_cast<uintptr_t>(prepared) & 15) == 0, BDETR_E_BAD_SHAPE, "prepared-targets buffer must be 16-byte aligned");
+    BDETR_REQUIRE(C <= 1024 && (long long)T * C < (1 << 22) && (long long)T * A < (1 << 22), BDETR_E_UNSUPPORTED, "C / T*C / T*A too large");
+    const CostBlobLayout BL = cost_blob_layout(T, C, A);
+    const size_t smem = cost_targets_smem(T, C, A, BL);
+    BDETR_REQUIRE(smem <= 227 * 1024, BDETR_E_UNSUPPORTED, "T*(C+A) too large for the shared-memory staging of the targets");
+    static size_t optin = 0;        // opt in to large dynamic shared memory once per size class (never during a later graph capture)
+    if (smem > optin) {
+        BDETR_CUDA(cudaFuncSetAttribute(cost_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        optin = smem;
+    }
+    launch_k(cost_targets_kernel, B, CM_THREADS, smem, as_stream(stream), T, C, A, cat_true, attr_true, box_true,
+             reinterpret_cast<unsigned char *>(prepared), BL);
+    BDETR_CHECK_LAUNCH("cost_targets_kernel");
+    return BDETR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int bdetr_cost_matrix_prepared(int B, int T, int Q, int C, int A, const void *prepared,
+                                     const float *cat_pred, const float *attr_pred, const float *box_pred,
+                                     float w_cat, float w_box, float w_attr, float *cost, void *stream)
+{
+    BDETR_REQUIRE(B > 0 && T > 0 && Q > 0 && C > 0 && A > 0, BDETR_E_BAD_SHAPE, "B,T,Q,C,A must be positive");
+    BDETR_REQUIRE(prepared && cat_pred && attr_pred && box_pred && cost, BDETR_E_NULL, "null pointer");
+    BDETR_REQUIRE((reinterpret_cast<uintptr_t>(prepared) & 15) == 0, BDETR_E_BAD_SHAPE, "prepared-targets buffer must be 16-byte aligned");
+    BDETR_REQUIRE(C <= 1024 && CM_QT * (long long)C < (1 << 20), BDETR_E_UNSUPPORTED, "C too large");
+    const bool has_attr = (w_attr != 0.0f);
+    const bool small_a = A <= CM_SMALL_A;
+    const CostSmemLayout L = cost_smem_layout(T, C, A, has_attr);
+    const CostBlobLayout BL = cost_blob_layout(T, C, A);
+    BDETR_REQUIRE(L.bytes <= 227 * 1024, BDETR_E_UNSUPPORTED, "C/A/T too large for the shared-memory tile");
+    dim3 grid(ceil_div(Q, CM_QT), B);
+    const int variant = has_attr ? (small_a ? 1 : 2) : 0;
+    auto kern = variant == 0 ? cost_matrix_kernel<false, true> : variant == 1 ? cost_matrix_kernel<true, true> : cost_matrix_kernel<true, false>;
+    static size_t optin[3] = {0, 0, 0};
+    if (L.bytes > optin[variant]) {
+        BDETR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
+        optin[variant] = L.bytes;
+    }
+    const f32x2 neg_zero_pair = 0x8000000080000000ull;
+    launch_k(kern, grid, CM_THREADS, L.bytes, as_stream(stream),
+             T, Q, C, A, reinterpret_cast<const unsigned char *>(prepared), cat_pred, attr_pred, box_pred, w_cat, w_box, w_attr, cost, L, BL, neg_zero_pair);
+    BDETR_CHECK_LAUNCH("cost_matrix_kernel");
+    return BDETR_OK;
+}
+
+// Convenience form of the two calls above with a library-owned, grow-only scratch buffer for the prepared targets.
+// The buffer is allocated on first use / growth (do that outside CUDA-graph capture) and shared by all calls on the
+// device: NOT for concurrent use from several streams -- callers that overlap matchers (the model does) hold their own
+// buffer and use bdetr_cost_targets_prepare + bdetr_cost_matrix_prepared.
 extern "C" __attribute__((visibility("default"))) int bdetr_cost_matrix_fwd(int B, int T, int Q, int C, int A,
                                      const float *cat_true, const float *attr_true, const float *box_true,
                                      const float *cat_pred, const float *attr_pred, const float *box_pred,
                                      float w_cat, float w_box, float w_attr, float *cost, void *stream)
 {
     BDETR_REQUIRE(B > 0 && T > 0 && Q > 0 && C > 0 && A > 0, BDETR_E_BAD_SHAPE, "B,T,Q,C,A must be positive");
-    BDETR_REQUIRE(cat_true && attr_true && box_true && cat_pred && attr_pred && box_pred && cost, BDETR_E_NULL, "null pointer");
-    const bool has_attr = (w_attr != 0.0f);
-    const CostSmemLayout L = cost_smem_layout(T, C, A, has_attr);
-    BDETR_REQUIRE(L.bytes <= 227 * 1024, BDETR_E_UNSUPPORTED, "C/A/T too large for the shared-memory tile");
-    dim3 grid(ceil_div(Q, CM_QT), B);
-    // opt in to large dynamic shared memory once per size class (never during a later graph capture)
-    static size_t optin[2] = {0, 0};
-    if (L.bytes > optin[has_attr]) {
-        if (has_attr) BDETR_CUDA(cudaFuncSetAttribute(cost_matrix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
-        else BDETR_CUDA(cudaFuncSetAttribute(cost_matrix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
-        optin[has_attr] = L.bytes;
+    static void *scratch[16] = {nullptr};
+    static size_t scratch_bytes[16] = {0};
+    int dev = 0;
+    BDETR_CUDA(cudaGetDevice(&dev));
+    BDETR_REQUIRE(dev >= 0 && dev < 16, BDETR_E_UNSUPPORTED, "device index out of range");
+    const size_t need = bdetr_cost_targets_bytes(B, T, C, A);
+    if (need > scratch_bytes[dev]) {
+        BDETR_CUDA(cudaStreamSynchronize(as_stream(stream)));
+        if (scratch[dev]) BDETR_CUDA(cudaFree(scratch[dev]));
+        scratch[dev] = nullptr; scratch_bytes[dev] = 0;
+        BDETR_CUDA(cudaMalloc(&scratch[dev], need));
+        scratch_bytes[dev] = need;
     }
-    if (has_attr) {
-        launch_k(cost_matrix_kernel<true>, grid, CM_THREADS, L.bytes, as_stream(stream), 
-            T, Q, C, A, cat_true, attr_true, box_true, cat_pred, attr_pred, box_pred, w_cat, w_box, w_attr, cost, L);
-    } else {
-        launch_k(cost_matrix_kernel<false>, grid, CM_THREADS, L.bytes, as_stream(stream), 
-            T, Q, C, A, cat_true, attr_true, box_true, cat_pred, attr_pred, box_pred, w_cat, w_box, w_attr, cost, L);
-    }
-    BDETR_CHECK_LAUNCH("cost_matrix_kernel");
-    return BDETR_OK;
+    const int rc = bdetr_cost_targets_prepare(B, T, C, A, cat_true, attr_true, box_true, scratch[dev], stream);
+    if (rc != BDETR_OK) return rc;
+    return bdetr_cost_matrix_prepared(B, T, Q, C, A, scratch[dev], cat_pred, attr_pred, box_pred, w_cat, w_box, w_attr, cost, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) size_t bdetr_lsap_smem_bytes(int T, int Q)

@@ -40,14 +40,30 @@ def raise_for_status(status: torch.Tensor) -> None:
         raise ValueError("cost matrix is infeasible")
 
 
-def pairwise_cost(y_true, y_pred, w_cat, w_box, w_attr):
+class PreparedTargets:
+    """Target side of the cost matrix, digested once (bdetr_cost_targets_prepare) and reusable against any number of
+    prediction sets of the same batch -- the boosted model matches ONE target batch at every block."""
+
+    def __init__(self, y_true):
+        category, attribute, bbox = (f32(t) for t in y_true[:3])
+        self.B, self.T, self.C = category.shape
+        self.A = attribute.shape[2]
+        self.true = (category, attribute, bbox)
+        nbytes = _lib.load().bdetr_cost_targets_bytes(self.B, self.T, self.C, self.A)
+        self.buffer = torch.empty(nbytes, dtype=torch.uint8, device=category.device)
+        _lib.call("bdetr_cost_targets_prepare", self.B, self.T, self.C, self.A, ptr(category), ptr(attribute), ptr(bbox),
+                  ptr(self.buffer), stream_ptr())
+
+
+def pairwise_cost(y_true, y_pred, w_cat, w_box, w_attr, prepared=None):
     """Weighted [B,T,Q] matching cost (reference MatchingLoss.call :119-130)."""
-    category, attribute, bbox = (f32(t) for t in y_true[:3])
     cat_preds, attr_preds, box_preds = (f32(t) for t in y_pred)
-    B, T, C = category.shape
-    Q, A = cat_preds.shape[1], attribute.shape[2]
+    if prepared is None:
+        prepared = PreparedTargets(y_true)
+    B, T, C, A = prepared.B, prepared.T, prepared.C, prepared.A
+    Q = cat_preds.shape[1]
     cost = empty(B, T, Q)
-    _lib.call("bdetr_cost_matrix_fwd", B, T, Q, C, A, ptr(category), ptr(attribute), ptr(bbox),
+    _lib.call("bdetr_cost_matrix_prepared", B, T, Q, C, A, ptr(prepared.buffer),
               ptr(cat_preds), ptr(attr_preds), ptr(box_preds), float(w_cat), float(w_box), float(w_attr),
               ptr(cost), stream_ptr())
     return cost
@@ -140,15 +156,16 @@ class MatchingLoss:
         self.MatchingMetric = MatchingMetric()
         self.check_status = True      # poll the device status flag after each call (set False inside graphs)
 
-    def forward(self, y_true, y_pred):
-        """Device-only forward; returns a context dict for `backward` (no host sync)."""
+    def forward(self, y_true, y_pred, prepared=None):
+        """Device-only forward; returns a context dict for `backward` (no host sync).  `prepared` = PreparedTargets of
+        y_true when the caller matches the same targets several times."""
         category, attribute, bbox = (f32(t) for t in y_true[:3])
         num_objects = i32(y_true[3].reshape(-1))
         cat_preds, attr_preds, box_preds = (f32(t) for t in y_pred)
         B, T, C = category.shape
         Q, A = cat_preds.shape[1], attribute.shape[2]
         w = (self.category_weight, self.box_weight, self.attribute_weight, self.exist_weight)
-        cost = pairwise_cost([category, attribute, bbox], [cat_preds, attr_preds, box_preds], w[0], w[1], w[2])
+        cost = pairwise_cost([category, attribute, bbox], [cat_preds, attr_preds, box_preds], w[0], w[1], w[2], prepared)
         col4row, row4col, _, _, status = self.MatchingMask.MatchingAssignment.assign(
             cost, num_objects, want_mask=False, want_assigned=False)
         losses = empty(5, B)

@@ -74,6 +74,23 @@ int bdetr_cost_matrix_fwd(int B, int T, int Q, int C, int A,
                           float w_cat, float w_box, float w_attr,
                           float *cost, void *stream);
 
+/* The same computation split in two, for callers that match the SAME targets against several prediction sets (the
+ * boosted model: one target batch, N blocks) or that run matchers concurrently on several streams:
+ *   bdetr_cost_targets_prepare  digests the target side once (class / attribute bit sets, class slots, hoisted box
+ *                               invariants, padding-row detection) into `prepared`, a caller-owned device buffer of
+ *                               bdetr_cost_targets_bytes(B,T,C,A) bytes, 16-byte aligned;
+ *   bdetr_cost_matrix_prepared  builds cost[B,T,Q] from it; bit-identical to bdetr_cost_matrix_fwd.
+ * bdetr_cost_matrix_fwd itself is these two calls on a library-owned grow-only scratch buffer (allocated on first use,
+ * outside graph capture; one buffer per device, so not for concurrent use from several streams). */
+size_t bdetr_cost_targets_bytes(int B, int T, int C, int A);
+int bdetr_cost_targets_prepare(int B, int T, int C, int A,
+                               const float *cat_true, const float *attr_true, const float *box_true,
+                               void *prepared, void *stream);
+int bdetr_cost_matrix_prepared(int B, int T, int Q, int C, int A, const void *prepared,
+                               const float *cat_pred, const float *attr_pred, const float *box_pred,
+                               float w_cat, float w_box, float w_attr,
+                               float *cost, void *stream);
+
 /* Per-image rectangular linear sum assignment on cost[b, :num_objects[b], :]; results are
  * bit-identical to scipy.optimize.linear_sum_assignment (ties included).
  * Replaces MatchingAssignment.scipy_linear_assignment_mask (:234-245) and MatchingMask.call

@@ -42,13 +42,16 @@ def main():
         losses = torch.empty(5, B, device="cuda"); iou = torch.empty(Q, device="cuda")
         s = stream_ptr()
         f_cost = lambda: _lib.call("bdetr_cost_matrix_fwd", B, T, Q, C, A, ptr(d[0]), ptr(d[1]), ptr(d[2]), ptr(d[4]), ptr(d[5]), ptr(d[6]), 1000.0, 1.0, w_attr, ptr(cost), s)
+        prep = torch.empty(_lib.load().bdetr_cost_targets_bytes(B, T, C, A), dtype=torch.uint8, device="cuda")
+        f_prep = lambda: _lib.call("bdetr_cost_targets_prepare", B, T, C, A, ptr(d[0]), ptr(d[1]), ptr(d[2]), ptr(prep), s)
+        f_cost_p = lambda: _lib.call("bdetr_cost_matrix_prepared", B, T, Q, C, A, ptr(prep), ptr(d[4]), ptr(d[5]), ptr(d[6]), 1000.0, 1.0, w_attr, ptr(cost), s)
         f_lsap = lambda: _lib.call("bdetr_lsap_assign", B, T, Q, ptr(cost), ptr(d[3]), ptr(c4r), ptr(r4c), ptr(mask), ptr(asg), ptr(st), s)
         f_lsap_nomask = lambda: _lib.call("bdetr_lsap_assign", B, T, Q, ptr(cost), ptr(d[3]), ptr(c4r), ptr(r4c), None, None, ptr(st), s)
         f_loss = lambda: _lib.call("bdetr_matched_loss_fwd", B, T, Q, C, A, ptr(d[0]), ptr(d[1]), ptr(d[2]), ptr(d[3]), ptr(d[4]), ptr(d[5]), ptr(d[6]), ptr(c4r), ptr(r4c), 1000.0, 1.0, w_attr, 100.0, ptr(losses), ptr(iou), s)
-        t_cost = timeit(f_cost); t_lsap = timeit(f_lsap); t_lsap2 = timeit(f_lsap_nomask); t_loss = timeit(f_loss)
+        t_cost = timeit(f_cost); t_prep = timeit(f_prep); t_cost_p = timeit(f_cost_p); t_lsap = timeit(f_lsap); t_lsap2 = timeit(f_lsap_nomask); t_loss = timeit(f_loss)
         bytes_cost = 4 * B * (Q * C + Q * A + 4 * Q + T * C + T * A + 4 * T + T * Q)
         key = f"B{B}_T{T}_Q{Q}_C{C}_A{A}_wattr{w_attr}"
-        out[key] = {"cost_us": t_cost, "cost_GBps": bytes_cost / t_cost / 1e3, "lsap_with_mask_us": t_lsap,
+        out[key] = {"cost_us": t_cost, "cost_GBps": bytes_cost / t_cost / 1e3, "targets_prepare_us": t_prep, "cost_prepared_us": t_cost_p, "lsap_with_mask_us": t_lsap,
                     "lsap_index_only_us": t_lsap2, "lsap_us_per_image": t_lsap2 / B, "matched_loss_us": t_loss}
         # CPU: the reference's literal loop (scipy, single thread)
         from scipy.optimize import linear_sum_assignment
