@@ -349,17 +349,28 @@ cost_targets_kernel(int T, int C, int A, const float *__restrict__ cat_true, con
     __syncthreads();
     mbar_wait(bar, 0);
 
-    for (int t = warp; t < T; t += CM_WARPS) {
-        for (int k = 0; k < CW; ++k) {
-            const int c = (k << 5) + lane;
-            const uint32_t bits = __ballot_sync(0xffffffffu, c < C && st_c[t * C + c] != 0.0f);
-            if (lane == 0) { cbits[t * CW + k] = bits; if (bits) atomicOr(&present[k], bits); }
+    {
+        // lane k keeps bit word k of the current row (one coalesced store per row) and the OR over this warp's rows
+        uint32_t seen = 0u;
+#pragma unroll 2
+        for (int t = warp; t < T; t += CM_WARPS) {
+            uint32_t mine = 0u;
+            for (int k = 0; k < CW; ++k) {
+                const int c = (k << 5) + lane;
+                const uint32_t bits = __ballot_sync(0xffffffffu, c < C && st_c[t * C + c] != 0.0f);
+                if (lane == k) mine = bits;
+            }
+            if (lane < CW) cbits[t * CW + lane] = mine;
+            seen |= mine;
+            mine = 0u;
+            for (int k = 0; k < AW; ++k) {
+                const int a = (k << 5) + lane;
+                const uint32_t bits = __ballot_sync(0xffffffffu, a < A && st_a[t * A + a] != 0.0f);
+                if (lane == k) mine = bits;
+            }
+            if (lane < AW) abits[t * AW + lane] = mine;
         }
-        for (int k = 0; k < AW; ++k) {
-            const int a = (k << 5) + lane;
-            const uint32_t bits = __ballot_sync(0xffffffffu, a < A && st_a[t * A + a] != 0.0f);
-            if (lane == 0) abits[t * AW + k] = bits;
-        }
+        if (lane < CW && seen) atomicOr(&present[lane], seen);
     }
     __syncthreads();
     // class -> slot (rank among the classes that occur in this image), slot -> class
@@ -970,7 +981,7 @@ extern "C" __attribute__((visibility("default"))) int bdetr_cost_targets_prepare
     BDETR_REQUIRE(B > 0 && T > 0 && C > 0 && A > 0, BDETR_E_BAD_SHAPE, "B,T,C,A must be positive");
     BDETR_REQUIRE(cat_true && attr_true && box_true && prepared, BDETR_E_NULL, "null pointer");
     BDETR_REQUIRE((reinterpret_cast<uintptr_t>(prepared) & 15) == 0, BDETR_E_BAD_SHAPE, "prepared-targets buffer must be 16-byte aligned");
-    BDETR_REQUIRE(C <= 1024 && (long long)T * C < (1 << 22) && (long long)T * A < (1 << 22), BDETR_E_UNSUPPORTED, "C / T*C / T*A too large");
+    BDETR_REQUIRE(C <= 1024 && A <= 1024 && (long long)T * C < (1 << 22) && (long long)T * A < (1 << 22), BDETR_E_UNSUPPORTED, "C / A / T*C / T*A too large");
     const CostBlobLayout BL = cost_blob_layout(T, C, A);
     const size_t smem = cost_targets_smem(T, C, A, BL);
     BDETR_REQUIRE(smem <= 227 * 1024, BDETR_E_UNSUPPORTED, "T*(C+A) too large for the shared-memory staging of the targets");
