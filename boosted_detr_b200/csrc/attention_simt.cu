@@ -230,7 +230,7 @@ int launch_attention_fwd(int B, int H, int Lq, int Lk, int d, const float *qp, c
     if (current_mode() == BDETR_MODE_TF32 && attention_umma_eligible(B, H, Lq, Lk, d, qp, kp, vp)) {
         // long sequences: three query tiles per CTA against a shared K/V ring (attention_umma_ms.cu)
         const int force = g_force_attention_kernel;
-        if (force == 2 || (force == 0 && attention_umma_ms_eligible(B, H, Lq, Lk)))
+        if (force == 2 || (force >= 20 && force <= 28) || (force == 0 && attention_umma_ms_eligible(B, H, Lq, Lk)))
             return launch_attention_fwd_umma_ms(B, H, Lq, Lk, d, qp, kp, vp, o, lse, round_out, s);
         return launch_attention_fwd_umma(B, H, Lq, Lk, d, qp, kp, vp, o, lse, round_out, s);
     }

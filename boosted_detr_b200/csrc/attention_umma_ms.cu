@@ -33,7 +33,31 @@ constexpr uint32_t MS_TMEM_COLS = 512;
 constexpr uint32_t MS_STREAM_COLS = 160;
 constexpr uint32_t MS_O_COL = 128;
 constexpr float MS_TH = 8.0f;      // log2 slack before the softmax reference maximum is raised
+constexpr int MS_POLY_DEFAULT = 2;  // of every 8 groups of exponentials, how many run on the FMA pipe
 
+// exp2 on the FMA pipe for a share of the elements.  With head dim 32 the softmax needs one exponential per 128
+// tensor-core flops; the MUFU does 16 per clock per SM, the tcgen05 pipe ~30 score elements per clock in tf32, so the
+// MUFU -- not the tensor pipe -- is the bound (ncu r1b: XU 65 %, tensor 33 %).  Groups of four elements selected by
+// POLY_MASK (bit g = group g of every 8) are evaluated as 2^x = 2^round(x) * p(x - round(x)) with a degree-3 minimax p
+// (max relative error 8.0e-5 = 2^-13.6, below the 2^-11 of the tf32 weights P is truncated to) in packed FADD2 / FFMA2
+// plus one LEA per element for the exponent; the rest still goes through MUFU.EX2.
+__device__ __forceinline__ void exp2_poly_x2(float x0, float x1, uint32_t &r0, uint32_t &r1)
+{
+    x0 = fmaxf(x0, -125.0f); x1 = fmaxf(x1, -125.0f);                  // masked (-inf) / far-away scores: ~2^-125, never a wrapped exponent
+    const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);       // 1.5 * 2^23: x + magic has round(x) in its low mantissa bits
+    const uint64_t X = pack_f32x2(x0, x1);
+    const uint64_t T = add_f32x2(X, magic);
+    const uint64_t F = sub_f32x2(X, sub_f32x2(T, magic));              // x - round(x) in [-0.5, 0.5]
+    uint64_t P = fma_f32x2(F, pack_f32x2(0.05519810691475868f, 0.05519810691475868f), pack_f32x2(0.24267712235450745f, 0.24267712235450745f));
+    P = fma_f32x2(P, F, pack_f32x2(0.6932618021965027f, 0.6932618021965027f));
+    P = fma_f32x2(P, F, pack_f32x2(0.9999227523803711f, 0.9999227523803711f));
+    float p0, p1, t0, t1;
+    unpack_f32x2(P, p0, p1); unpack_f32x2(T, t0, t1);
+    r0 = __float_as_uint(p0) + (__float_as_uint(t0) << 23);              // low bits of t = round(x) (two's complement): add to the exponent
+    r1 = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
+}
+
+template <uint32_t POLY_MASK>
 __global__ void __launch_bounds__(MS_THREADS, 1)
 attention_fwd_umma_ms_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                              const __grid_constant__ CUtensorMap map_v, int H, int Lq, int Lk,
@@ -229,10 +253,18 @@ attention_fwd_umma_ms_kernel(const __grid_constant__ CUtensorMap map_q, const __
                         float x0, x1, x2, x3;
                         unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sc2, nm2), x0, x1);
                         unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])), sc2, nm2), x2, x3);
-                        cur[i] = __float_as_uint(ex2_approx(x0)) & 0xFFFFE000u;
-                        cur[i + 1] = __float_as_uint(ex2_approx(x1)) & 0xFFFFE000u;
-                        cur[i + 2] = __float_as_uint(ex2_approx(x2)) & 0xFFFFE000u;
-                        cur[i + 3] = __float_as_uint(ex2_approx(x3)) & 0xFFFFE000u;
+                        if ((POLY_MASK >> ((i >> 2) & 7)) & 1u) {         // compile-time choice per group: FMA-pipe exponential
+                            uint32_t e0, e1, e2, e3;
+                            exp2_poly_x2(x0, x1, e0, e1);
+                            exp2_poly_x2(x2, x3, e2, e3);
+                            cur[i] = e0 & 0xFFFFE000u; cur[i + 1] = e1 & 0xFFFFE000u;
+                            cur[i + 2] = e2 & 0xFFFFE000u; cur[i + 3] = e3 & 0xFFFFE000u;
+                        } else {
+                            cur[i] = __float_as_uint(ex2_approx(x0)) & 0xFFFFE000u;
+                            cur[i + 1] = __float_as_uint(ex2_approx(x1)) & 0xFFFFE000u;
+                            cur[i + 2] = __float_as_uint(ex2_approx(x2)) & 0xFFFFE000u;
+                            cur[i + 3] = __float_as_uint(ex2_approx(x3)) & 0xFFFFE000u;
+                        }
                         ps_a = add_f32x2(ps_a, pack_f32x2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])));
                         ps_b = add_f32x2(ps_b, pack_f32x2(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])));
                     }
@@ -295,14 +327,22 @@ int launch_attention_fwd_umma_ms(int B, int H, int Lq, int Lk, int d, const floa
     ok = ok && encode_tensor_map_2d(&mv, vp, (long long)B * Lk, D, D, MS_HD, MS_KT, true);
     BDETR_REQUIRE(ok, BDETR_E_CUDA, "cuTensorMapEncodeTiled failed");
     const size_t smem = (size_t)(MS_NS + 2 * MS_STAGES) * MS_TILE_BYTES + 32 * 8 + 16 + 1024;
-    static bool optin = false;
-    if (!optin) {
-        BDETR_CUDA(cudaFuncSetAttribute(attention_fwd_umma_ms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        optin = true;
+    // share of exponentials evaluated on the FMA pipe: groups of 4 elements per 32 (bdetr_debug_force_attention_kernel
+    // 20 + n selects n of 8 for experiments; the default was chosen from gpurun_out/bench_attention.json)
+    const int share = (g_force_attention_kernel >= 20 && g_force_attention_kernel <= 28) ? g_force_attention_kernel - 20 : MS_POLY_DEFAULT;
+    auto kern = share == 0 ? attention_fwd_umma_ms_kernel<0x00u> : share == 1 ? attention_fwd_umma_ms_kernel<0x10u>
+              : share == 2 ? attention_fwd_umma_ms_kernel<0x22u> : share == 3 ? attention_fwd_umma_ms_kernel<0x4Au>
+              : share == 4 ? attention_fwd_umma_ms_kernel<0xAAu> : share == 5 ? attention_fwd_umma_ms_kernel<0xB5u>
+              : share == 6 ? attention_fwd_umma_ms_kernel<0xDDu> : share == 7 ? attention_fwd_umma_ms_kernel<0xEFu>
+              : attention_fwd_umma_ms_kernel<0xFFu>;
+    static bool optin[9] = {false};
+    if (!optin[share]) {
+        BDETR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        optin[share] = true;
     }
     const float scale_log2 = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
     dim3 grid(ceil_div(Lq, MS_NS * MS_BM), H, B);
-    launch_k(attention_fwd_umma_ms_kernel, grid, MS_THREADS, smem, s, mq, mk, mv, H, Lq, Lk, o, lse, scale_log2, round_out, g_umma_timeline);
+    launch_k(kern, grid, MS_THREADS, smem, s, mq, mk, mv, H, Lq, Lk, o, lse, scale_log2, round_out, g_umma_timeline);
     BDETR_CHECK_LAUNCH("attention_fwd_umma_ms_kernel");
     return BDETR_OK;
 }

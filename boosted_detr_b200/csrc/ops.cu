@@ -159,7 +159,8 @@ API int bdetr_accumulate(size_t n, const float *x, float *y, void *stream)
 }
 API int bdetr_debug_force_attention_kernel(int which)
 {
-    BDETR_REQUIRE(which >= 0 && which <= 2, BDETR_E_UNSUPPORTED, "0 auto, 1 one tile per CTA, 2 multi-stream");
+    BDETR_REQUIRE((which >= 0 && which <= 2) || (which >= 20 && which <= 28), BDETR_E_UNSUPPORTED,
+                  "0 auto, 1 one tile per CTA, 2 multi-stream, 20 + n multi-stream with n of 8 exponential groups on the FMA pipe");
     bdetr::g_force_attention_kernel = which;
     return BDETR_OK;
 }

@@ -207,6 +207,12 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b)
+{
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 // maximum of 32 floats held as raw bits: a 4-level tree of 3-input maxima (16 instructions, depth 4)
 __device__ __forceinline__ float max32_tree(const uint32_t v[32])
 {

@@ -19,6 +19,8 @@ for mode_name, mode in (("tf32", _lib.MODE_TF32), ("fp32", _lib.MODE_FP32)):
         fn = lambda: _lib.call("bdetr_attention_core_fwd", B, H, Lq, Lk, d, ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), stream_ptr())
         # tensor-core mode, long sequences: time both schedules (1 = one tile per CTA, 2 = three streams per CTA)
         variants = (1, 2) if (mode_name == "tf32" and Lq >= 1000) else (0,)
+        if mode_name == "tf32" and Lq >= 20000:
+            variants = (1, 20, 21, 22, 23, 24, 25, 26, 28)        # 20 + n: n of 8 exponential groups on the FMA pipe
         for which in variants:
             lib.bdetr_debug_force_attention_kernel(which)
             for _ in range(3):
