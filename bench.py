@@ -27,6 +27,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CFG = dict(N=6, B=16, rows=20, cols=20, Q=100, T=20, D=256, H=8)
 METRIC = "images/sec fwd+bwd+matcher"
+# dram__bytes_read.sum + dram__bytes_write.sum of one gemm_umma_kernel<128,...> launch at [6400,256]x[256,256]
+# (profiles/r1b_ncu_full_kernels.csv, ncu --set full): 13.39 MB read (A 6.55 MB + cold weights / L2 flush residue), 0 written
+# back before the kernel ended; algorithmic bytes are 13.4 MB (read A, write C) -- no wasted re-reads.
+NCU_DRAM_BYTES_GEMM = 13.39e6
 
 
 def synth_batch(rank, B, C, A, cfg=CFG):
@@ -51,6 +55,9 @@ def make_model(cfg=CFG, seed=0):
     w["DecoderPrep/init_decoder_features"] = rng.normal(0, 0.02, w["DecoderPrep/init_decoder_features"].shape).astype(np.float32)
     model.set_weights_dict(w)
     model.dropout_seed = 2024                                               # training-mode dropout (rate .1) is on
+    # the reference's optimizer (Boosted_DETR_COCO.ipynb cell 26): the timed step ends with its update
+    from boosted_detr_b200.optimizers import SGD, CosineDecayRestarts
+    model.compile(optimizer=SGD(learning_rate=CosineDecayRestarts(1e-3, 4000, m_mul=.95, alpha=.1), momentum=.9, nesterov=True, clipnorm=0.1))
     return model
 
 
@@ -150,7 +157,8 @@ def roofline_block(cfg, B, flush, peaks):
     ach = flops_gemm / t_gemm / 1e12
     return {"bound": "tensor", "kernel": "gemm_umma_kernel (Dense forward [%d,%d]x[%d,%d], tf32 operands)" % (M, D, D, D) if mode else
             "gemm_simt_kernel (Dense forward [%d,%d]x[%d,%d], fp32 FFMA)" % (M, D, D, D),
-            "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None, "peak_source": src,
+            "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+            "traffic": NCU_DRAM_BYTES_GEMM if (mode and (M, D) == (6400, 256)) else None, "peak_source": src,
             "us_per_launch": t_gemm * 1e6, "mode": "tf32" if mode else "fp32",
             "note": "peak is the measured bf16 cuBLAS figure; TF32 tensor peak is half of it. K=256 makes this GEMM "
                     "latency / L2-ingest bound (see profiles/README.md)",
@@ -198,10 +206,17 @@ def cpu_reference_steps(cfg, B, C, A, steps, warmup, threads):
     batch = synth_batch(0, B, C, A, cfg)
     tg = (batch["category"], batch["attribute"], batch["bbox"], batch["num_objects"])
     times = []
+    acc = {}
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        R.train_step_reference(w, batch["features"], tg, N, cfg["H"], torch.float32, dropout_seed=2024,
-                               weights=R.model_weights(1.0))
+        _, grads, stats = R.train_step_reference(w, batch["features"], tg, N, cfg["H"], torch.float32, dropout_seed=2024,
+                                                 weights=R.model_weights(1.0))
+        if not acc:
+            acc = {k: np.zeros_like(v, dtype=np.float32) for k, v in grads.items()}
+        lr = R.cosine_decay_restarts(it, 1e-3, 4000, 2.0, .95, .1)
+        new_w, acc = R.sgd_step_reference({k: w[k] for k in grads}, grads, acc, lr, .9, True, .1, dtype=np.float32)
+        w.update(new_w)
+        w.update({k: np.asarray(v, np.float32) for k, v in stats.items()})
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -227,7 +242,8 @@ def main():
     cfg, B = CFG, CFG["B"]
     workload = (f"BASELINE config 2: Boosted DETR default, {cfg['N']} enc/dec pairs, d_model {cfg['D']}, {cfg['H']} heads, "
                 f"{cfg['Q']} queries, {cfg['rows']}x{cfg['cols']} features (640x640/32), batch {B}/GPU, T={cfg['T']}, C={C}, A={A}, "
-                "training step = fwd + Hungarian loss at every block + bwd (+ grad all-reduce when N>1), dropout .1 on")
+                "training step = fwd + Hungarian loss at every block + bwd (+ grad all-reduce when N>1) + SGD-Nesterov update "
+                "(per-variable clipnorm .1, CosineDecayRestarts), dropout .1 on")
     config = {"workload": workload, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
               "l2": "flushed between timed steps (256 MiB write outside the event brackets); per-step CUDA events"}
     cores = os.cpu_count() or 1

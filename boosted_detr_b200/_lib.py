@@ -71,6 +71,7 @@ PROTOTYPES = {
     "bdetr_add_positional_bwd": (c_int, [I, I, I, P, P, P]),
     "bdetr_tile_queries_fwd": (c_int, [I, I, I, P, P, P]),
     "bdetr_accumulate": (c_int, [c_size_t, P, P, P]),
+    "bdetr_sgd_step": (c_int, [I, P, P, P, P, P, F, P, F, I, F, P]),
     "bdetr_round_tf32": (c_int, [c_size_t, P, P, P]),
     "bdetr_debug_set_timeline": (c_int, [P]),
     "bdetr_debug_force_attention_kernel": (c_int, [I]),

@@ -21,6 +21,8 @@ class GraphedTrainStep:
         self.static = {"features": feats.clone(), "category": y_true[0].clone(), "attribute": y_true[1].clone(),
                        "bbox": y_true[2].clone(), "num_objects": y_true[3].clone()}
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.static.values())
+        if model.optimizer is not None:
+            model.optimizer.prepare(model)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -30,10 +32,10 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.metrics, self.status = self._step()
+            self.metrics, self.status = self._step(capturing=True)
         torch.cuda.synchronize()
 
-    def _step(self):
+    def _step(self, capturing=False):
         m = self.model
         s = self.static
         m.zero_grads()
@@ -44,6 +46,11 @@ class GraphedTrainStep:
         m._join_metrics()
         if m.grad_bucket_hook is not None and m.grad_allreduce is not None:
             m.grad_allreduce(m._flat[1])          # joins the bucketed all-reduces issued inside the backward (captured too)
+        # the optimizer update belongs to the graph whenever the gradients are final inside it (single GPU, or the
+        # bucketed all-reduce above); its learning rate is read from device memory (see SGD.capture / pre_replay)
+        self.optimizer_in_graph = m.optimizer is not None and (m.grad_allreduce is None or m.grad_bucket_hook is not None)
+        if self.optimizer_in_graph and capturing:
+            m.optimizer.capture(m)
         return metrics, m.status_all
 
     def load(self, inputs):
@@ -63,11 +70,13 @@ class GraphedTrainStep:
                 dst.copy_(m._pinned(k, x, dtype).reshape(dst.shape), non_blocking=True)
 
     def replay(self):
-        self.graph.replay()
         m = self.model
+        if self.optimizer_in_graph:
+            m.optimizer.pre_replay()
+        self.graph.replay()
         if m.grad_allreduce is not None and m.grad_bucket_hook is None:
             m.grad_allreduce(m._flat[1])          # non-overlapped mode: one all-reduce after the graph
-        if m.optimizer is not None:
+        if m.optimizer is not None and not self.optimizer_in_graph:
             m.optimizer.apply(m)
         m.step_count += 1
 

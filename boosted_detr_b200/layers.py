@@ -48,17 +48,31 @@ def he_normal(rng, fan_in, fan_out):
 
 class Layer:
     _rng = np.random.default_rng(0)
+    trainable_epoch = 0            # bumped whenever any layer's `trainable` flag is written (optimizer table cache key)
 
     def __init__(self, name=None, **kwargs):
         self.name = name or type(self).__name__
         self.built = False
-        self.trainable = True
+        self._trainable = True
         self._weights: dict[str, torch.Tensor] = {}
         self._grads: dict[str, torch.Tensor] = {}
         self._non_trainable: set[str] = set()
         self._shadow: dict[str, torch.Tensor] = {}     # tf32-rounded copies of the Dense kernels (tensor-core mode)
         self._struct_cache = None
         self.last_ctx = None
+
+    # Keras semantics: setting `trainable` on a layer sets it on all of its sublayers (the reference freezes whole
+    # boosted blocks this way, Boosted_DETR_COCO.ipynb cell 30); the optimizer skips variables of frozen layers.
+    @property
+    def trainable(self):
+        return self._trainable
+
+    @trainable.setter
+    def trainable(self, value):
+        self._trainable = bool(value)
+        Layer.trainable_epoch += 1
+        for sub in self.sublayers():
+            sub.trainable = value
 
     # -- weights ---------------------------------------------------------------------------
     def add_weight(self, name: str, value: np.ndarray, trainable: bool = True) -> torch.Tensor:

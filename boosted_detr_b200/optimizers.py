@@ -1,0 +1,152 @@
+"""Optimizer and learning-rate schedule of the reference's training runs, on the flat weight / gradient buffers.
+
+Reference: /root/reference/Boosted_DETR_COCO.ipynb cell 26 / 30
+    lr = tf.keras.optimizers.schedules.CosineDecayRestarts(initial_learning_rate=.001, first_decay_steps=4000,
+                                                           m_mul=.95, alpha=0.1)
+    tf.keras.optimizers.SGD(learning_rate=lr, momentum=.9, nesterov=True, clipnorm=0.1)
+and the per-block `layer.trainable = True / False` freezing schedule of cell 30 (frozen variables are left out of the
+chunk table, so they are neither clipped nor updated).  The update itself is bdetr_sgd_step (csrc/optimizer.cu).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device import ptr, stream_ptr, zeros
+
+CHUNK = 16384
+
+
+class CosineDecayRestarts:
+    """tf.keras.optimizers.schedules.CosineDecayRestarts (SGDR), evaluated in float32 like TensorFlow does."""
+
+    def __init__(self, initial_learning_rate, first_decay_steps, t_mul=2.0, m_mul=1.0, alpha=0.0, name=None):
+        self.initial_learning_rate = float(initial_learning_rate)
+        self.first_decay_steps = int(first_decay_steps)
+        self.t_mul, self.m_mul, self.alpha = float(t_mul), float(m_mul), float(alpha)
+        self.name = name
+
+    def __call__(self, step: int) -> float:
+        f = np.float32
+        completed = f(step) / f(self.first_decay_steps)
+        t_mul, m_mul, alpha = f(self.t_mul), f(self.m_mul), f(self.alpha)
+        if self.t_mul == 1.0:
+            i_restart = np.floor(completed)
+            completed = completed - i_restart
+        else:
+            i_restart = np.floor(np.log(f(1.0) - completed * (f(1.0) - t_mul)) / np.log(t_mul))
+            sum_r = (f(1.0) - t_mul ** i_restart) / (f(1.0) - t_mul)
+            completed = (completed - sum_r) / t_mul ** i_restart
+        m_fac = m_mul ** i_restart
+        cosine_decayed = f(0.5) * m_fac * (f(1.0) + np.cos(f(math.pi) * completed))
+        decayed = (f(1.0) - alpha) * cosine_decayed + alpha
+        return float(f(self.initial_learning_rate) * decayed)
+
+    def get_config(self):
+        return {"initial_learning_rate": self.initial_learning_rate, "first_decay_steps": self.first_decay_steps,
+                "t_mul": self.t_mul, "m_mul": self.m_mul, "alpha": self.alpha, "name": self.name}
+
+
+class SGD:
+    """tf.keras.optimizers.SGD(learning_rate, momentum, nesterov, clipnorm) for BoostedDETR.compile()."""
+
+    def __init__(self, learning_rate=0.01, momentum=0.0, nesterov=False, clipnorm=None, name="SGD", **kwargs):
+        if kwargs:
+            raise TypeError(f"unsupported SGD arguments: {sorted(kwargs)}")
+        self.learning_rate = learning_rate
+        self.momentum = float(momentum)
+        self.nesterov = bool(nesterov)
+        self.clipnorm = None if clipnorm is None else float(clipnorm)
+        self.name = name
+        self.iterations = 0
+        self._table_key = None
+        self._table = None
+        self._accum = None
+
+    def current_lr(self) -> float:
+        lr = self.learning_rate
+        return float(lr(self.iterations)) if callable(lr) else float(lr)
+
+    # -- chunk table over the trainable variables ------------------------------------------------
+    @staticmethod
+    def trainable_slots(model):
+        """(name, offset, count) of every variable the optimizer updates, in flat-buffer order."""
+        slots = []
+        for name, owner, key in model.named_weights():
+            if key in owner._non_trainable or not owner.trainable or name not in model._index:
+                continue
+            off, cnt, _ = model._index[name]
+            slots.append((name, off, cnt))
+        slots.sort(key=lambda s: s[1])
+        return slots
+
+    @staticmethod
+    def chunk_table(slots) -> np.ndarray:
+        rows = []
+        for _, off, cnt in slots:
+            n = max(1, -(-cnt // CHUNK))
+            first = len(rows)
+            for c in range(n):
+                lo = c * CHUNK
+                rows.append((off + lo, min(CHUNK, cnt - lo), first, n, 0))
+        dt = np.dtype([("offset", "<i8"), ("len", "<i4"), ("var_first", "<i4"), ("var_chunks", "<i4"), ("reserved", "<i4")])
+        return np.array(rows, dtype=dt) if rows else np.zeros(0, dtype=dt)
+
+    def _ensure_table(self, model):
+        from .layers import Layer
+        key = (id(model._flat[0]), Layer.trainable_epoch)
+        if key != self._table_key:
+            tab = self.chunk_table(self.trainable_slots(model))
+            dev = model._flat[0].device
+            self._table = torch.from_numpy(tab.view(np.uint8).copy()).to(dev)
+            self._n_chunks = len(tab)
+            self._partial = zeros(max(1, len(tab)))
+            self._table_key = key
+        if self._accum is None or self._accum.numel() != model._flat[0].numel():
+            self._accum = zeros(model._flat[0].numel())       # Keras slot "momentum", one per variable, flat like the weights
+
+    def _launch(self, model, lr, lr_dev):
+        _lib.call("bdetr_sgd_step", self._n_chunks, ptr(self._table), ptr(model._flat[0]), ptr(model._flat[1]),
+                  ptr(self._accum), ptr(self._partial), lr, lr_dev, self.momentum, int(self.nesterov),
+                  0.0 if self.clipnorm is None else self.clipnorm, stream_ptr())
+
+    def apply(self, model):
+        """One optimizer step on model's flat buffers with the gradients currently in them (after any all-reduce)."""
+        if model._flat is None:
+            raise RuntimeError("build the model before applying the optimizer")
+        self._ensure_table(model)
+        lr = self.current_lr()
+        self._launch(model, lr, None)
+        self.iterations += 1
+        self.last_lr = lr
+
+    # -- CUDA-graph form: the update kernels are captured once and read the step's rate from device memory -------
+    def prepare(self, model):
+        """Allocations and host->device copies of the chunk table: must happen OUTSIDE graph capture."""
+        self._ensure_table(model)
+        if getattr(self, "_lr_dev", None) is None:
+            self._lr_dev = zeros(1)
+            self._lr_host = torch.zeros(16, dtype=torch.float32).pin_memory()    # ring: the host may run a few steps ahead
+
+    def capture(self, model):
+        """Call inside graph capture (after the gradients are final; `prepare` first).  The table is frozen into the
+        graph: changing `trainable` flags afterwards needs a new capture."""
+        self._launch(model, 0.0, ptr(self._lr_dev))
+
+    def pre_replay(self):
+        """Before every replay of a graph that contains `capture`: evaluates the schedule for this step and queues the
+        4-byte pinned H2D copy of the rate on the current stream."""
+        lr = self.current_lr()
+        slot = self.iterations % 16
+        self._lr_host[slot] = lr
+        self._lr_dev.copy_(self._lr_host[slot:slot + 1], non_blocking=True)
+        self.iterations += 1
+        self.last_lr = lr
+
+    def get_config(self):
+        lr = self.learning_rate
+        return {"name": self.name, "learning_rate": lr.get_config() if hasattr(lr, "get_config") else float(lr),
+                "momentum": self.momentum, "nesterov": self.nesterov, "clipnorm": self.clipnorm}

@@ -268,6 +268,30 @@ int bdetr_debug_force_attention_kernel(int which);
 int bdetr_gemm(int M, int N, int K, const float *A, int transA, const float *Bm, int transB,
                const float *bias, int act, int beta, float *C, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Optimizer step: Keras SGD with momentum / Nesterov and per-variable clipnorm, the optimizer of
+ * the reference's training runs (Boosted_DETR_COCO.ipynb cells 26, 30:
+ * tf.keras.optimizers.SGD(learning_rate=lr, momentum=.9, nesterov=True, clipnorm=0.1)).
+ *   g <- (g * clipnorm) / max(||g||_2, clipnorm) per variable  (tf.clip_by_norm; clipnorm <= 0 disables it)
+ *   accum <- momentum * accum - lr * g ;  var += nesterov ? momentum * accum - lr * g : accum
+ * The trainable variables are described by a DEVICE table of chunks (<= 16384 elements each, a variable = a run of
+ * consecutive table entries) over the flat weight / gradient / accumulator buffers; frozen variables are simply left
+ * out of the table.  `partial` = n_chunks floats of workspace.  The schedule (CosineDecayRestarts, ...) is evaluated by
+ * the host side; the step's learning rate is the plain argument `lr`, or -- when `lr_dev` is not NULL -- the float it
+ * points to in device memory (so that a captured CUDA graph can be replayed with a new rate every step).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    long long offset;     /* first element of the chunk in the flat buffers */
+    int len;              /* elements in the chunk */
+    int var_first;        /* table index of the first chunk of the variable this chunk belongs to */
+    int var_chunks;       /* number of chunks of that variable */
+    int reserved;
+} bdetr_opt_chunk;
+
+int bdetr_sgd_step(int n_chunks, const bdetr_opt_chunk *chunks,
+                   float *weights, const float *grads, float *accum, float *partial,
+                   float lr, const float *lr_dev, float momentum, int nesterov, float clipnorm, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -472,3 +472,41 @@ def train_step_reference(params, features, targets, num_blocks, num_heads, dtype
     grads = {k: (v.grad.detach().numpy() if v.grad is not None else np.zeros(v.shape))
              for k, v in p.items() if v.requires_grad}
     return out, grads, {k: v.numpy() for k, v in new_stats.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+# Optimizer of the reference's training runs (/root/reference/Boosted_DETR_COCO.ipynb cells 26, 30):
+#   tf.keras.optimizers.SGD(learning_rate=CosineDecayRestarts(.001, 4000, m_mul=.95, alpha=.1),
+#                           momentum=.9 | .95, nesterov=True, clipnorm=0.1)
+# TensorFlow is not installable here: restated from the published TF 2.x semantics (PARITY UNPINNED), in float64 so
+# that the product's float32 arithmetic is checked against something more accurate than itself.
+# ---------------------------------------------------------------------------------------------
+def cosine_decay_restarts(step, initial_learning_rate, first_decay_steps, t_mul=2.0, m_mul=1.0, alpha=0.0):
+    """tf.keras.optimizers.schedules.CosineDecayRestarts.__call__ (SGDR, Loshchilov & Hutter)."""
+    completed = step / first_decay_steps
+    if t_mul == 1.0:
+        i_restart = math.floor(completed)
+        completed -= i_restart
+    else:
+        i_restart = math.floor(math.log(1.0 - completed * (1.0 - t_mul)) / math.log(t_mul))
+        sum_r = (1.0 - t_mul ** i_restart) / (1.0 - t_mul)
+        completed = (completed - sum_r) / t_mul ** i_restart
+    m_fac = m_mul ** i_restart
+    cosine_decayed = 0.5 * m_fac * (1.0 + math.cos(math.pi * completed))
+    return initial_learning_rate * ((1.0 - alpha) * cosine_decayed + alpha)
+
+
+def sgd_step_reference(variables: dict, grads: dict, accums: dict, lr, momentum, nesterov, clipnorm, dtype=np.float64):
+    """One Keras SGD step over named numpy arrays (updated copies returned).  clipnorm is PER VARIABLE
+    (tf.clip_by_norm: g * c / max(||g||, c)); momentum form of ResourceApplyKerasMomentum.  dtype float64 for parity
+    checks, float32 (TensorFlow's own arithmetic) when the step is being timed."""
+    new_v, new_a = {}, {}
+    lr, momentum = dtype(lr), dtype(momentum)
+    for k, w in variables.items():
+        g = np.asarray(grads[k], dtype)
+        if clipnorm is not None:
+            g = g * dtype(clipnorm / max(float(np.sqrt(np.dot(g.ravel(), g.ravel()))), clipnorm))
+        a = np.asarray(accums[k], dtype) * momentum - lr * g
+        new_a[k] = a
+        new_v[k] = np.asarray(w, dtype) + (a * momentum - lr * g if nesterov else a)
+    return new_v, new_a
