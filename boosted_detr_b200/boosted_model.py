@@ -214,6 +214,15 @@ class BoostedDETR:
             self._side = torch.cuda.Stream()
         return self._side
 
+    def _loss_streams(self, n):
+        if not _lib.load().bdetr_get_concurrency():
+            return [self._side_stream()] * n
+        cur = getattr(self, "_loss_s", [])
+        while len(cur) < n:
+            cur.append(torch.cuda.Stream())
+        self._loss_s = cur
+        return cur[:n]
+
     def _aux_streams(self):
         """Four extra streams: two for the attribute / box heads (the three heads of a block are independent
         chains of short kernels), one for the batch-invariant decoder self-attention, one for the decoder chain."""
@@ -222,6 +231,15 @@ class BoostedDETR:
         if getattr(self, "_aux", None) is None:
             self._aux = [torch.cuda.Stream() for _ in range(4)]
         return self._aux
+
+    # -- timeline of one captured step (tests/trace_step.py): timing events that survive CUDA-graph capture -------
+    def _mark(self, label, stream=None):
+        tr = getattr(self, "_trace", None)
+        if tr is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True, external=True)
+        ev.record(stream if stream is not None else torch.cuda.current_stream())
+        tr.append((label, ev))
 
     # -- forward -------------------------------------------------------------------------------
     def forward(self, feats, y_true, training):
@@ -255,6 +273,12 @@ class BoostedDETR:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 prepared = PreparedTargets(y_true)
+            # The matching of block i (cost -> per-image assignment -> matched loss) only depends on block i's running
+            # prediction, and the sequential solver dominates it (~0.2 ms on near-tied early-training predictions), so
+            # every block gets its own stream: the six matchings overlap instead of forming a 1.2 ms chain.
+            loss_streams = self._loss_streams(N)
+            for ls in loss_streams:
+                ls.wait_stream(side)
         for i in range(N):
             keys = self._keys(i) if use_dropout else None
             enc = self.EncoderTransformerBlocks[i]
@@ -274,12 +298,14 @@ class BoostedDETR:
                     dec0 = self.DecoderPrep.tile_queries(x.shape[0], like=x)
                     pre_self = dec_l.SelfAttentionBlock.forward([dec0, dec0, dec0], training, dkeys[0])
             (x, pos), c_enc = enc.forward([x], training, keys["enc"] if keys else None)
+            self._mark(f"fwd enc{i} done (main)")
             dec_s.wait_stream(main)
             with torch.cuda.stream(dec_s):
                 prep_out, c_prep = self.DecoderPrep.forward([x, pos], training, dec=dec0)
                 if pre_self is not None:
                     dec_s.wait_stream(aux[2])
                 dec, c_dec = dec_l.forward(list(prep_out), training, dkeys, pre_self=pre_self)
+                self._mark(f"fwd dec{i} done (dec)")
                 mult = 2.0 if i == 0 else 1.0                 # block 0 is counted twice (reference :222-229)
                 if cums is not None and training:
                     cums = [c.clone() for c in cums]          # each block's loss keeps its own running prediction
@@ -295,16 +321,22 @@ class BoostedDETR:
                     new_cums.append(c["cum"])
                 dec_s.wait_stream(aux[0])
                 dec_s.wait_stream(aux[1])
+                self._mark(f"fwd heads{i} done (dec)")
                 cums = new_cums
                 blocks.append({"enc": c_enc, "prep": c_prep, "dec": c_dec, "heads": c_heads})
                 if training:
-                    side.wait_stream(dec_s)
-                    with torch.cuda.stream(side):
+                    ls = loss_streams[i]
+                    ls.wait_stream(dec_s)
+                    with torch.cuda.stream(ls):
                         loss_ctxs.append(self.loss_fn.forward(y_true, cums, prepared))
+                        self._mark(f"fwd loss{i} done (side)")
         main.wait_stream(dec_s)
         main.wait_stream(aux[2])
         if training:
             main.wait_stream(side)
+            for ls in loss_streams:
+                main.wait_stream(ls)
+        self._mark("fwd joined (main)")
         return cums, {"blocks": blocks, "loss": loss_ctxs, "y_true": y_true}
 
     def backward(self, ctx, gscale=1.0):
@@ -328,6 +360,7 @@ class BoostedDETR:
             for i in reversed(range(N)):
                 blk = ctx["blocks"][i]
                 self.loss_fn.backward(ctx["loss"][i], r_cat, r_attr, r_box, gscale)
+                self._mark(f"bwd loss{i} done (dec)")
                 # the three heads are independent: category on this stream, attribute / box beside it
                 aux[0].wait_stream(dec_s)
                 aux[1].wait_stream(dec_s)
@@ -340,6 +373,7 @@ class BoostedDETR:
                 dec_s.wait_stream(aux[1])
                 accumulate(d_dec_a, d_dec)
                 accumulate(d_dec_b, d_dec)
+                self._mark(f"bwd heads{i} done (dec)")
                 # decoder: FFN + cross-attention here; the self-attention backward (queries only) and the
                 # query-parameter gradient go to aux2
                 d_ev, d_s, d_ek = self.DecoderBlocks[i].backward(blk["dec"], d_dec, defer_self=True)
@@ -351,6 +385,7 @@ class BoostedDETR:
                     self_ev.record(aux[2])
                 ev = torch.cuda.Event()
                 ev.record(dec_s)
+                self._mark(f"bwd dec{i} done (dec)")
                 handoff[i] = (d_ev, d_ek, ev, self_ev)
                 keep += [d_dec, d_dec_a, d_dec_b, d_s, d_q, d_ev, d_ek]
         d_x_next = None
@@ -365,6 +400,7 @@ class BoostedDETR:
             g_pos = enc._grads["positional_encoding"].view(L, D)
             d_x4 = self.DecoderPrep.backward(blk["prep"], d_ev, None, d_ek, g_pos)
             d_x_next = enc.backward(blk["enc"], d_x4)
+            self._mark(f"bwd enc{i} done (main)")
             if self.grad_bucket_hook is not None and self._flat is not None:
                 # every gradient of boosted block i is final once this stream (encoder i, and through the hand-off
                 # event decoder i / heads i) and the self-attention stream have passed this point: its bucket can be
@@ -373,6 +409,7 @@ class BoostedDETR:
                 self.grad_bucket_hook(i, lo, hi, [self_ev])
         main.wait_stream(dec_s)
         main.wait_stream(aux[2])
+        self._mark("bwd joined (main)")
         return d_x_next
 
     # -- keras surface -------------------------------------------------------------------------

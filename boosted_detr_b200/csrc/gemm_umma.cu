@@ -10,6 +10,7 @@
 //     wgrad     dW[K,N] += X[M,K]^T dY[M,N]    A MN-major, B MN-major   (split-K, fp32 red.add)
 // One CTA computes one 128 x BN output tile (x one K split): warp 0 = TMA producer, warp 1 = TMEM
 // allocator + single-thread MMA issuer, warps 2-5 = epilogue (one TMEM lane = one output row each).
+#include <cstdlib>
 #include "umma.cuh"
 
 namespace bdetr {
@@ -262,6 +263,8 @@ bool encode_tensor_map_2d(CUtensorMap *map, const float *base, long long rows, i
     return r == CUDA_SUCCESS;
 }
 
+constexpr bool UMMA_SHALLOW_DEFAULT = true;
+
 template <int BN, int STAGES>
 static size_t umma_smem_bytes() { return (size_t)STAGES * (UM_BM * UM_BK * 4 + BN * UM_BK * 4) + (2 * STAGES + 1) * 8 + 64 + BN * 4 + 1024; }
 
@@ -272,13 +275,20 @@ bool umma_gemm_eligible(int M, int N, int K, const float *A, int lda, bool TA, c
     return ok(A, lda) && ok(B, ldb) && ldc % 4 == 0 && K >= 32 && N >= 64 && M >= 128;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_umma_inst(dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mc, const UmmaEpilogue &ep,
-                            cudaStream_t s)
+// Pipeline depth.  Deep = the whole K = 256 extent (8 k-blocks) in flight: lowest latency for ONE kernel (TMA round trips
+// are ~1000 cycles), but 192 KB of stages means one CTA per SM, so GEMMs of concurrently running chains (encoder /
+// decoder / heads backward on separate streams) queue for SMs.  Shallow = 96 KB (two CTAs per SM).  Selected once from
+// the environment (BDETR_UMMA_STAGES=deep|shallow); the default is what the whole-step benchmark favours.
+static bool umma_shallow()
 {
-    // The grids of this workload are at most one wave, so a CTA's latency is the kernel's latency: keep the whole
-    // K = 256 extent (8 k-blocks) in flight -- TMA round trips are ~1000 cycles.  192 KB of stages either way.
-    constexpr int STAGES = BN == 64 ? 8 : 6;
+    static const bool v = [] { const char *e = getenv("BDETR_UMMA_STAGES"); return e ? (e[0] == 's' || e[0] == 'S') : UMMA_SHALLOW_DEFAULT; }();
+    return v;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int launch_umma_stages(dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mc, const UmmaEpilogue &ep,
+                              cudaStream_t s)
+{
     static bool optin = false;
     const size_t smem = umma_smem_bytes<BN, STAGES>();
     if (!optin) {
@@ -288,6 +298,14 @@ static int launch_umma_inst(dim3 grid, const CUtensorMap &ma, const CUtensorMap 
     launch_k(gemm_umma_kernel<BN, STAGES, A_MN, B_MN>, grid, UM_THREADS, smem, s, ma, mb, mc, ep);
     BDETR_CHECK_LAUNCH("gemm_umma_kernel");
     return BDETR_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_umma_inst(dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mc, const UmmaEpilogue &ep,
+                            cudaStream_t s)
+{
+    if (umma_shallow()) return launch_umma_stages<BN, BN == 64 ? 4 : 3, A_MN, B_MN>(grid, ma, mb, mc, ep, s);
+    return launch_umma_stages<BN, BN == 64 ? 8 : 6, A_MN, B_MN>(grid, ma, mb, mc, ep, s);
 }
 
 // Same contract as launch_gemm (gemm_simt.cu).  TA: A stored [K,M]; TB: B stored [N,K].

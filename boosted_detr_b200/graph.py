@@ -31,8 +31,12 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        if getattr(model, "_trace", None) is not None:
+            model._trace.clear()                   # keep only the marks of the captured step
         with torch.cuda.graph(self.graph):
+            model._mark("step start (main)")
             self.metrics, self.status = self._step(capturing=True)
+            model._mark("step end (main)")
         torch.cuda.synchronize()
 
     def _step(self, capturing=False):

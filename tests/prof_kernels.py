@@ -32,5 +32,15 @@ mask = torch.empty(Bm, T, Q, device="cuda"); asg = torch.empty(Bm, Q, device="cu
 for _ in range(2):
     _lib.call("bdetr_cost_matrix_fwd", Bm, T, Q, C, A, ptr(d[0]), ptr(d[1]), ptr(d[2]), ptr(d[4]), ptr(d[5]), ptr(d[6]), 1000.0, 1.0, 1.0, ptr(cost), stream_ptr())
     _lib.call("bdetr_lsap_assign", Bm, T, Q, ptr(cost), ptr(d[3]), ptr(c4r), ptr(r4c), ptr(mask), ptr(asg), ptr(st), stream_ptr())
+# optimizer update at BASELINE config 2 size: 8.05 M parameters in ~300 variables
+from boosted_detr_b200.optimizers import SGD
+sizes = ([65536, 256] * 60 + [102400] * 6 + [256 * 82, 82, 1024, 4] * 6)
+sizes = sizes * max(1, 8_047_638 // sum(sizes))
+offs = np.cumsum([0] + [(n + 3) // 4 * 4 for n in sizes])
+tab = SGD.chunk_table([(str(i), int(offs[i]), n) for i, n in enumerate(sizes)])
+tab_d = torch.from_numpy(tab.view(np.uint8).copy()).cuda()
+wf = torch.randn(int(offs[-1]), device="cuda"); gf = torch.randn_like(wf) * 1e-3; af = torch.zeros_like(wf); part = torch.zeros(len(tab), device="cuda")
+for _ in range(2):
+    _lib.call("bdetr_sgd_step", len(tab), ptr(tab_d), ptr(wf), ptr(gf), ptr(af), ptr(part), 1e-3, None, 0.9, 1, 0.1, stream_ptr())
 torch.cuda.synchronize()
 print("ok")

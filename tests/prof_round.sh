@@ -8,8 +8,8 @@ python tests/prof_step.py tf32 > gpurun_out/${TAG}_step_plain.log 2>&1 || { echo
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/${TAG}_launches_tf32.csv python tests/prof_step.py tf32 > gpurun_out/${TAG}_step_ncu.log 2>&1
 python tests/prof_kernels.py tf32 > gpurun_out/${TAG}_kernels_plain.log 2>&1 || { echo "prof_kernels failed"; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:"gemm_umma|attention_fwd_umma|attention_bwd|cost_matrix|lsap_kernel" \
-    --launch-skip 20 --launch-count 14 -o gpurun_out/${TAG}_kernels -f python tests/prof_kernels.py tf32 > gpurun_out/${TAG}_kernels_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"gemm_umma|attention_fwd_umma|attention_bwd|cost_matrix|cost_targets|lsap_kernel|sgd_" \
+    --launch-skip 20 --launch-count 22 -o gpurun_out/${TAG}_kernels -f python tests/prof_kernels.py tf32 > gpurun_out/${TAG}_kernels_ncu.log 2>&1
 python tests/prof_attention.py > gpurun_out/${TAG}_attn_plain.log 2>&1 || { echo "prof_attention failed"; exit 1; }
 ncu --set full --clock-control none --import-source on -k regex:attention_fwd_umma_ms --launch-skip 2 --launch-count 1 \
     -o gpurun_out/${TAG}_attn_ms -f python tests/prof_attention.py > gpurun_out/${TAG}_attn_ncu.log 2>&1
