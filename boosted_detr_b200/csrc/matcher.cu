@@ -775,6 +775,163 @@ lsap_kernel(int T, int Q, const float *__restrict__ cost, const int32_t *__restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K8, register-resident form (n <= Q <= 32 * KMAX): the same shortest-augmenting-path solver, same fp64 expressions,
+// same tie rule, but the per-column state lives in REGISTERS -- lane l owns columns l, l + 32, ... and keeps their dual
+// v, shortest-path cost, owner row and position in scipy's swap-removed `remaining` list -- so a column scan has no
+// dependent shared-memory round trips, and the warp arg-min is three hardware warp reductions (REDUX on the high word
+// of an order-preserving 64-bit key of the cost, on its low word, on the tie rank) instead of fifteen shuffles.
+// The solver is a serial chain of scans (early-training predictions are near-tied in a way all targets agree on, which
+// drives it towards its n^2 / 2 worst case), so scan latency is the whole cost: ~1800 -> ~300 cycles per scan.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t f64_order_key(double x)
+{
+    const uint64_t b = (uint64_t)__double_as_longlong(x + 0.0);          // + 0.0: -0 and +0 compare equal, give them one key
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(32)
+lsap_reg_kernel(int T, int Q, const float *__restrict__ cost, const int32_t *__restrict__ num_objects,
+                int32_t *__restrict__ col4row_out, int32_t *__restrict__ row4col_out, int32_t *__restrict__ status,
+                int stage_cost, int validate)
+{
+    pdl_sync();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    double *u = reinterpret_cast<double *>(smem_raw);                       // [T]
+    int *path = reinterpret_cast<int *>(u + T);                             // [Q]
+    int *col4row = path + Q;                                                // [T]
+    float *cost_s = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(col4row + T) + 15) & ~uintptr_t(15));
+
+    int n = num_objects[b]; n = n < 0 ? 0 : (n > T ? T : n);
+    int32_t *c4r_o = col4row_out + (size_t)b * T;
+    int32_t *r4c_o = row4col_out + (size_t)b * Q;
+    for (int t = lane; t < T; t += 32) c4r_o[t] = -1;
+    for (int q = lane; q < Q; q += 32) r4c_o[q] = -1;
+    const float *cb = cost + (size_t)b * T * Q;
+    if (validate) {
+        // scipy's input check on the live rows, fused with the staging copy (staged problems only): NaN / -inf -> error
+        bool bad = false;
+        const int total = n * Q;
+        if ((reinterpret_cast<uintptr_t>(cb) & 15) == 0 && (total & 3) == 0) {
+            for (int e = lane; e < (total >> 2); e += 32) {
+                const float4 c4 = reinterpret_cast<const float4 *>(cb)[e];
+                reinterpret_cast<float4 *>(cost_s)[e] = c4;
+                bad = bad || c4.x != c4.x || c4.y != c4.y || c4.z != c4.z || c4.w != c4.w ||
+                      c4.x == -CUDART_INF_F || c4.y == -CUDART_INF_F || c4.z == -CUDART_INF_F || c4.w == -CUDART_INF_F;
+            }
+        } else {
+            for (int e = lane; e < total; e += 32) { const float c = cb[e]; cost_s[e] = c; bad = bad || c != c || c == -CUDART_INF_F; }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) status[b] = bad ? BDETR_E_INVALID_COST : 0;
+        if (bad || n == 0) return;
+        cb = cost_s;
+    } else {
+        if (n == 0 || status[b] != 0) return;
+        if (stage_cost) {
+            const int total = n * Q;
+            for (int e = lane; e < total; e += 32) cost_s[e] = cb[e];
+            cb = cost_s;
+        }
+    }
+    for (int i = lane; i < n; i += 32) { u[i] = 0.0; col4row[i] = -1; }
+
+    double v[KMAX], spc[KMAX];
+    int r4c[KMAX], pos[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) { v[k] = 0.0; r4c[k] = -1; }
+    __syncwarp();
+
+    bool infeasible = false;
+    for (int cur = 0; cur < n; ++cur) {
+        double minVal = 0.0;
+        int i = cur, nrem = Q, sink = -1;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) { const int j = lane + 32 * k; pos[k] = j < Q ? Q - 1 - j : -1; spc[k] = CUDART_INF; }
+        while (sink == -1) {
+            const double ui = u[i];
+            const float *crow = cb + (size_t)i * Q;
+            float cc[KMAX];
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) cc[k] = pos[k] >= 0 ? crow[lane + 32 * k] : 0.0f;
+            double best_s = CUDART_INF;
+            int best_rank = -1, best_k = 0;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                if (pos[k] >= 0) {
+                    const double r = ((minVal + (double)cc[k]) - ui) - v[k];
+                    if (r < spc[k]) { path[lane + 32 * k] = i; spc[k] = r; }
+                    const double sk = spc[k];
+                    const int rank = (r4c[k] == -1) ? (RANK_FREE + pos[k]) : (RANK_USED - pos[k]);
+                    if (sk < best_s || (sk == best_s && rank > best_rank)) { best_s = sk; best_rank = rank; best_k = k; }
+                }
+            }
+            // warp arg-min of (cost ascending, rank descending): ranks are distinct, so exactly one lane wins
+            const uint64_t key = f64_order_key(best_s);
+            const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+            const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+            const bool c1 = hi == mhi;
+            const uint32_t mlo = __reduce_min_sync(0xffffffffu, c1 ? lo : 0xffffffffu);
+            const bool c2 = c1 && lo == mlo;
+            const int mrank = __reduce_max_sync(0xffffffffu, c2 ? best_rank : -1);
+            if (mrank < 0) { infeasible = true; break; }                 // every remaining column is +inf (rank -1 = no column)
+            const uint32_t win = __ballot_sync(0xffffffffu, c2 && best_rank == mrank);
+            const int wl = __ffs(win) - 1;
+            // the winner's column: its cost, owner row, position and index k
+            int w_owner = 0, w_pos = 0;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) if (k == best_k) { w_owner = r4c[k]; w_pos = pos[k]; }
+            minVal = __shfl_sync(0xffffffffu, best_s, wl);
+            if (minVal == CUDART_INF) { infeasible = true; break; }
+            const int packed = __shfl_sync(0xffffffffu, (best_k << 16) | w_pos, wl);
+            const int owner = __shfl_sync(0xffffffffu, w_owner, wl);
+            const int index = packed & 0xffff, wk = packed >> 16;
+            const int j = wl + 32 * wk;
+            // swap-remove: the column at the end of the list takes the freed position, the winner leaves the list
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                if (pos[k] == nrem - 1) pos[k] = index;
+                if (lane == wl && k == wk) pos[k] = -2;                  // -2 = scanned and removed in this search (the set SC)
+            }
+            --nrem;
+            if (owner == -1) sink = j; else i = owner;
+        }
+        if (infeasible) break;
+        // dual updates (same fp64 expressions as the sequential solver).  Every visited row other than `cur` is the owner
+        // of exactly one removed column, so the row update is done from the column side.
+        if (lane == 0) u[cur] = u[cur] + minVal;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (pos[k] == -2) {
+                const int r = r4c[k];
+                if (r >= 0) u[r] = u[r] + (minVal - spc[k]);
+                v[k] = v[k] - (minVal - spc[k]);
+            }
+        }
+        __syncwarp();
+        // augment along the stored path (uniform walk; the owner registers are patched by their lanes)
+        {
+            int j = sink;
+            for (;;) {
+                const int r = path[j];
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) if (lane + 32 * k == j) r4c[k] = r;
+                const int tmp = col4row[r];
+                __syncwarp();
+                if (lane == 0) col4row[r] = j;
+                __syncwarp();
+                j = tmp;
+                if (r == cur) break;
+            }
+        }
+        __syncwarp();
+    }
+    if (infeasible) { if (lane == 0) status[b] = BDETR_E_INFEASIBLE; return; }
+    for (int i = lane; i < n; i += 32) { const int j = col4row[i]; c4r_o[i] = j; r4c_o[j] = i; }
+}
+
 // mask [B,T,Q] and assigned [B,Q] from the index form: the bandwidth-bound part of K8.
 __global__ void lsap_mask_kernel(int B, int T, int Q, const int32_t *__restrict__ col4row,
                                  const int32_t *__restrict__ row4col, float *__restrict__ mask,
@@ -1069,22 +1226,40 @@ extern "C" __attribute__((visibility("default"))) int bdetr_lsap_assign(int B, i
     // small cost matrices are staged in shared memory (latency-bound regime); large ones stay in L2 so that many
     // images fit on an SM
     const int stage = ((size_t)T * Q * sizeof(float) <= 48 * 1024) ? 1 : 0;
-    if (stage) smem += (size_t)T * Q * sizeof(float) + 16;
     cudaStream_t s = as_stream(stream);
-    BDETR_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * B, s));
-    {
+    // Register-resident solver whenever no image can need scipy's transposed path (T <= Q) and a lane's share of the
+    // columns fits its registers; staged problems also validate their own rows (no memset / validate launches).
+    const bool reg_form = T <= Q && Q <= 320;
+    const bool fused_validate = reg_form && stage;
+    if (!fused_validate) {
+        BDETR_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * B, s));
         const size_t total = (size_t)B * T * Q;
         const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
         launch_k(lsap_validate_kernel, blocks, 256, 0, s, B, T, Q, cost, num_objects, status);
         BDETR_CHECK_LAUNCH("lsap_validate_kernel");
     }
-    static size_t lsap_optin = 0;
-    if (smem > lsap_optin) {
-        BDETR_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        lsap_optin = smem;
+    if (reg_form) {
+        size_t rsmem = (size_t)T * (sizeof(double) + sizeof(int)) + (size_t)Q * sizeof(int) + 16;
+        if (stage) rsmem += (size_t)T * Q * sizeof(float);
+        auto kern = Q <= 128 ? lsap_reg_kernel<4> : lsap_reg_kernel<10>;
+        static size_t reg_optin[2] = {0, 0};
+        const int which = Q <= 128 ? 0 : 1;
+        if (rsmem > 48 * 1024 && rsmem > reg_optin[which]) {
+            BDETR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+            reg_optin[which] = rsmem;
+        }
+        launch_k(kern, B, 32, rsmem, s, T, Q, cost, num_objects, col4row, row4col, status, stage, fused_validate ? 1 : 0);
+        BDETR_CHECK_LAUNCH("lsap_reg_kernel");
+    } else {
+        if (stage) smem += (size_t)T * Q * sizeof(float) + 16;
+        static size_t lsap_optin = 0;
+        if (smem > lsap_optin) {
+            BDETR_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            lsap_optin = smem;
+        }
+        launch_k(lsap_kernel, B, 32, smem, s, T, Q, cost, num_objects, col4row, row4col, status, stage);
+        BDETR_CHECK_LAUNCH("lsap_kernel");
     }
-    launch_k(lsap_kernel, B, 32, smem, s, T, Q, cost, num_objects, col4row, row4col, status, stage);
-    BDETR_CHECK_LAUNCH("lsap_kernel");
     if (mask || assigned) {
         const size_t total = (size_t)B * T * Q / 4 + 1;
         const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
