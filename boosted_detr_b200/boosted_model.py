@@ -354,11 +354,14 @@ class BoostedDETR:
         aux = self._aux_streams()
         dec_s = aux[3]
         keep = [r_cat, r_attr, r_box]            # buffers used on other streams stay alive until the final join
-        handoff = [None] * N
         dec_s.wait_stream(main)
-        with torch.cuda.stream(dec_s):
-            for i in reversed(range(N)):
-                blk = ctx["blocks"][i]
+        d_x_next = None
+        # The two chains are ENQUEUED interleaved, block by block (decoder side of block i, then encoder i on main):
+        # stream semantics do not care, but a captured graph is scheduled roughly in node-creation order, and with the
+        # whole decoder-side chain created first the encoder chain of block N-1 sat idle behind it (measured: +0.5 ms).
+        for i in reversed(range(N)):
+            blk = ctx["blocks"][i]
+            with torch.cuda.stream(dec_s):
                 self.loss_fn.backward(ctx["loss"][i], r_cat, r_attr, r_box, gscale)
                 self._mark(f"bwd loss{i} done (dec)")
                 # the three heads are independent: category on this stream, attribute / box beside it
@@ -386,13 +389,9 @@ class BoostedDETR:
                 ev = torch.cuda.Event()
                 ev.record(dec_s)
                 self._mark(f"bwd dec{i} done (dec)")
-                handoff[i] = (d_ev, d_ek, ev, self_ev)
                 keep += [d_dec, d_dec_a, d_dec_b, d_s, d_q, d_ev, d_ek]
-        d_x_next = None
-        for i in reversed(range(N)):
-            blk = ctx["blocks"][i]
-            d_ev, d_ek, ev, self_ev = handoff[i]
             main.wait_event(ev)
+            self._mark(f"bwd enc{i} may start (main)")
             if d_x_next is not None:
                 accumulate(d_x_next.reshape(d_ev.shape), d_ev)
             enc = self.EncoderTransformerBlocks[i]

@@ -185,6 +185,9 @@ class FeedForwardBlock(Layer):
         return d_x
 
 
+TRACE_HOOK = None          # tests/trace_step.py: callable(label) dropping a timing event on the current stream
+
+
 def add_positional(x, pos):
     B, L, D = x.shape
     out = torch.empty_like(x)
@@ -225,7 +228,11 @@ class EncoderBlock(Layer):
     def backward(self, ctx, d_out, d_pos):
         """Returns d_x; accumulates the positional gradient (summed over the batch) into d_pos."""
         d_a = self.FeedForwardBlock.backward(ctx["ffn"], d_out)
+        if TRACE_HOOK is not None:
+            TRACE_HOOK(f"  {self.name} ffn bwd done (main)")
         d_xp, _, d_x = self.SelfAttentionBlock.backward(ctx["attn"], d_a)   # d_key aliases d_query (same tensor)
+        if TRACE_HOOK is not None:
+            TRACE_HOOK(f"  {self.name} attn bwd done (main)")
         batch_sum_into(d_xp, d_pos)
         accumulate(d_xp, d_x)
         return d_x

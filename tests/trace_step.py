@@ -13,6 +13,9 @@ lib = _lib.load(); lib.bdetr_set_mode(_lib.MODE_TF32 if mode == "tf32" else _lib
 model = bench.make_model(bench.CFG)
 batch = bench.synth_batch(0, bench.CFG["B"], 82, 3, bench.CFG)
 model._trace = []
+if "--fine" in sys.argv:
+    from boosted_detr_b200 import transformers
+    transformers.TRACE_HOOK = model._mark
 gs = GraphedTrainStep(model, batch)
 marks = list(model._trace)
 model._trace = None
