@@ -235,7 +235,15 @@ def main():
     ap.add_argument("--no-conc", action="store_true", help="disable multi-stream concurrency inside the step (A/B timing)")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch (A/B timing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-seconds", type=float, default=900.0, help="hard wall-clock limit: a wedged run exits 3 instead of hanging")
     args = ap.parse_args()
+
+    def _watchdog():
+        time.sleep(args.max_seconds)
+        sys.stderr.write(f"bench.py: exceeded --max-seconds {args.max_seconds:.0f}, aborting\n")
+        sys.stderr.flush()
+        os._exit(3)
+    threading.Thread(target=_watchdog, daemon=True).start()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     C, A = 82, 3
@@ -295,7 +303,8 @@ def main():
         step()
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:                                                # one nvidia-smi poller per job, not one per GPU
+        sampler.start()
     lib.bdetr_reset_launch_count()
     if args.no_graph:
         step(); torch.cuda.synchronize()
@@ -336,10 +345,11 @@ def main():
     h2d = sum(v.nbytes for v in batch.values())
     d2h = 4 * 6 + 4 * cfg["N"] * B                         # six metric means + per-block, per-image matcher status flags
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
 
     if rank != 0:
-        return
+        return                                                   # (no collective below this line: the other ranks are gone)
     if launches_per_step is None:
         # count by running one eager (non-graph) step
         dev_batch = {k: torch.from_numpy(v).cuda() for k, v in batch.items()}
