@@ -6,7 +6,9 @@ the TF-side formulas below are restated from the published behaviour of those li
 (Keras Dense / LayerNormalization / BatchNormalization / BinaryCrossentropy, tfa
 giou_loss and SigmoidFocalCrossEntropy).  PINNED: the assignment step calls the very
 function the reference calls, scipy.optimize.linear_sum_assignment
-(/root/reference/ModelComponents/losses_and_metrics.py:242).
+(/root/reference/ModelComponents/losses_and_metrics.py:242).  CROSS-CHECKED (tests/test_oracle_crosscheck.py):
+GIoU / IoU, focal loss, LayerNorm / BatchNorm / attention core, SGD-Nesterov + clipnorm and the cosine-restart
+schedule agree with the independent torchvision / torch implementations of the same published algorithms.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
 import this module; the product (boosted_detr_b200/) never does.
