@@ -22,6 +22,11 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
+            # The gradient buckets are ~5 MB and hidden under the backward, so ring / tree over NVLink P2P is all the
+            # bandwidth this path needs.  NVLS (in-switch reduction) is left off by default: its buffer registration
+            # inside CUDA-graph capture could not be validated on 4 / 8 GPUs in round 1 (export NCCL_NVLS_ENABLE=1 to
+            # try it).
+            os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         import datetime
         dist.init_process_group(backend=backend, rank=rank, world_size=world, timeout=datetime.timedelta(seconds=180))
     return rank, world, local
