@@ -330,7 +330,14 @@ def main():
     # them host->device and reads the metric means + matcher status back
     host_batch = {k: torch.from_numpy(np.ascontiguousarray(v, np.int32 if k == "num_objects" else np.float32)).pin_memory()
                   for k, v in batch.items()}
-    e2e_fn = (lambda: model.train_step(batch)) if args.no_graph else (lambda: gs(host_batch))
+    # BDETR_E2E_PREFETCH=1: the next step's H2D copy is queued under the running step (GraphedTrainStep.prefetch);
+    # off by default until it has been validated on the GPU
+    if args.no_graph:
+        e2e_fn = lambda: model.train_step(batch)
+    elif os.environ.get("BDETR_E2E_PREFETCH") == "1":
+        e2e_fn = lambda: gs(host_batch, prefetch=host_batch)
+    else:
+        e2e_fn = lambda: gs(host_batch)
     for _ in range(3):
         e2e_fn()
     barrier()
@@ -370,7 +377,7 @@ def main():
             "vs_baseline": None, "dtype": "tf32" if args.mode == "tf32" else "fp32", "data": "synthetic (random-init weights)",
             "config": config, "clocks": sampler.summary(),
             "e2e": {"value": B * world / e2e_sec, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_sec * 1e3},
+                    "ms_per_step": e2e_sec * 1e3, "input_prefetch": os.environ.get("BDETR_E2E_PREFETCH") == "1" and not args.no_graph},
             "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
             "cuda_graph": not args.no_graph, "pdl": not args.no_pdl, "allreduce": ("none" if world == 1 else "one call after backward" if args.no_overlap else "per-block buckets overlapped with backward, inside the CUDA graph"), "concurrent_streams": not args.no_conc, "loss": logs.get("loss") if isinstance(logs, dict) else None,
             "step_algorithmic_tflops": flops / sec_per_step / 1e12, "roofline": roof}

@@ -84,9 +84,46 @@ class GraphedTrainStep:
             m.optimizer.apply(m)
         m.step_count += 1
 
-    def __call__(self, inputs, return_host=True):
-        self.load(inputs)
+    # -- input prefetch (opt-in; NOT yet validated on the GPU: see DESIGN.md §7) -------------------------------------
+    def prefetch(self, inputs):
+        """Starts the H2D copy of the NEXT batch into a second set of device buffers on a copy stream, so that it runs
+        underneath the step that is executing; `__call__(inputs)` with the same object then only does device-to-device
+        copies.  The caller keeps `inputs` (pinned host tensors) alive and unmodified until that call."""
+        if not hasattr(self, "_staging"):
+            self._staging = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._copy_stream = torch.cuda.Stream()
+            self._staged_ev, self._staging_free = torch.cuda.Event(), torch.cuda.Event()
+            self._staging_free.record(torch.cuda.current_stream())
+            self._staged_for = None
+        cs = self._copy_stream
+        cs.wait_event(self._staging_free)                 # the previous staging -> static copy has run
+        with torch.cuda.stream(cs):
+            for k, dst in self._staging.items():
+                x = inputs[k]
+                if not (isinstance(x, torch.Tensor) and (x.is_cuda or x.is_pinned())):
+                    x = self.model._pinned(k, x, "i32" if k == "num_objects" else "f32")
+                dst.copy_(x.reshape(dst.shape), non_blocking=True)
+            self._staged_ev.record(cs)
+        self._staged_for = inputs
+
+    def _take_prefetched(self):
+        main = torch.cuda.current_stream()
+        main.wait_event(self._staged_ev)
+        for k, dst in self.static.items():
+            dst.copy_(self._staging[k], non_blocking=True)
+        self._staging_free.record(main)
+        self._staged_for = None
+
+    def __call__(self, inputs, return_host=True, prefetch=None):
+        """One training step on `inputs`.  `prefetch` = the batch of the FOLLOWING step (optional): its H2D copy is
+        queued right behind this step's launch and overlaps with it."""
+        if getattr(self, "_staged_for", None) is inputs and inputs is not None:
+            self._take_prefetched()
+        else:
+            self.load(inputs)
         self.replay()
+        if prefetch is not None:
+            self.prefetch(prefetch)
         if not return_host:
             return self.metrics
         return self.model.host_logs()
