@@ -139,10 +139,15 @@ int launch_gemm(int M, int N, int K, const float *A, int lda, bool TA, const flo
     g.vecB = aligned16(B) && (ldb % 4 == 0);
     const int tiles = ceil_div(M, GBM) * ceil_div(N, GBN);
     int splits = 1;
-    // Few output tiles (the prediction heads' [1600,256]x[256,N<=82] and their weight gradients): the K loop is the
-    // kernel's latency (~1 us per 16-deep step), so K is cut into chunks of >= 64 across up to two waves of CTAs.
-    if (act == 0 && relu_mask == nullptr && !round_out && tiles < 96 && K >= 128) {
-        splits = min(ceil_div(K, 64), max(1, 296 / tiles));
+    // Few output tiles: the K loop is the kernel's latency (~1 us per 16-deep step), so K is cut across CTAs and the
+    // partial sums meet in atomics.  Accumulating calls (the prediction heads' weight gradients, [256,1600]x[1600,N<=82])
+    // split down to 64-deep chunks across up to two waves of CTAs.  NON-accumulating calls keep the old K >= 512 rule:
+    // the heads' forward GEMM (K = 256) must stay unsplit, because atomics make the summation order -- hence the last
+    // bit -- differ between rows, and identical query rows (the reference's zero-initialised queries at step 0) must
+    // give bit-identical predictions for the matcher's tie rule to reproduce the reference's assignment.
+    if (act == 0 && relu_mask == nullptr && !round_out && tiles < 96) {
+        if (beta && K >= 128) splits = min(ceil_div(K, 64), max(1, 296 / tiles));
+        else if (K >= 512) splits = min(ceil_div(K, 256), max(1, 296 / tiles));
     }
     g.k_chunk = ceil_div(ceil_div(K, splits), GBK) * GBK;
     splits = ceil_div(K, g.k_chunk);
