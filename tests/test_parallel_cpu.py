@@ -1,6 +1,6 @@
-"""world_size-2 gloo tests of the data-parallel host logic: shard by image, per-replica
+"""world_size-2 and -4 gloo tests of the data-parallel host logic: shard by image, per-replica
 BatchNorm / loss normaliser, loss scaled by 1/replicas, gradients summed by all-reduce.  The oracle is the
-checker: the all-reduced per-replica gradients must equal a single-process emulation of the two replicas."""
+checker: the all-reduced per-replica gradients must equal a single-process emulation of the replicas."""
 import os
 import socket
 import sys
@@ -58,8 +58,11 @@ def _free_port():
     return p
 
 
-def test_two_replicas_match_single_process_emulation():
-    world = 2
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_replicas_match_single_process_emulation(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
