@@ -235,7 +235,7 @@ def main():
     ap.add_argument("--no-conc", action="store_true", help="disable multi-stream concurrency inside the step (A/B timing)")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch (A/B timing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--max-seconds", type=float, default=900.0, help="hard wall-clock limit: a wedged run exits 3 instead of hanging")
+    ap.add_argument("--max-seconds", type=float, default=420.0, help="hard wall-clock limit: a wedged run exits 3 instead of hanging")
     args = ap.parse_args()
 
     def _watchdog():
