@@ -4,7 +4,7 @@ GPU access -- run it under a `timeout` first).  6 enc/dec pairs, 100 queries, 4 
     2.6 TFLOP per image), and
   * the reference-faithful size: 1333 x 800 at the backbone's stride 32 = 41 x 25 = 1 025 tokens.
 Prints images/s, ms per batch and the algorithmic TFLOP/s (SURVEY 8d formulas), timed with CUDA events after warm-up.
-usage: python tests/bench_hires.py [B per GPU, default 4]"""
+usage: python bench_tools/bench_hires.py [B per GPU, default 4]"""
 import json, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

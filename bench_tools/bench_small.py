@@ -1,6 +1,6 @@
 """In-graph (no host launch gaps) timings of the small latency-bound kernels at BASELINE config 2 (not a pytest file)."""
 import os, sys, numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from util import synth_preds, synth_targets
 from boosted_detr_b200 import _lib
 from boosted_detr_b200.device import ptr, stream_ptr

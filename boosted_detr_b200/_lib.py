@@ -58,14 +58,14 @@ PROTOTYPES = {
     "bdetr_lsap_smem_bytes": (c_size_t, [I, I]),
     "bdetr_matched_loss_fwd": (c_int, [I, I, I, I, I, P, P, P, P, P, P, P, P, P, F, F, F, F, P, P, P]),
     "bdetr_matched_loss_bwd": (c_int, [I, I, I, I, I, P, P, P, P, P, P, P, P, P, F, F, F, F, F, P, P, P, P]),
-    "bdetr_attention_block_fwd": (c_int, [I, I, I, I, I, P, P, P, POINTER(AttnParams), F, c_uint32, F, P,
+    "bdetr_attention_block_fwd": (c_int, [I, I, I, I, I, P, P, P, POINTER(AttnParams), F, c_uint32, P, F, P,
                                           POINTER(AttnSaved), P]),
     "bdetr_attention_core_fwd": (c_int, [I, I, I, I, I, P, P, P, P, P, P]),
-    "bdetr_attention_block_bwd": (c_int, [I, I, I, I, I, P, P, P, POINTER(AttnParams), F, c_uint32,
+    "bdetr_attention_block_bwd": (c_int, [I, I, I, I, I, P, P, P, POINTER(AttnParams), F, c_uint32, P,
                                           POINTER(AttnSaved), P, P, P, P, I, POINTER(AttnParams),
                                           POINTER(AttnScratch), P]),
-    "bdetr_ffn_block_fwd": (c_int, [I, I, P, POINTER(FfnParams), F, c_uint32, F, P, POINTER(FfnSaved), P]),
-    "bdetr_ffn_block_bwd": (c_int, [I, I, P, POINTER(FfnParams), F, c_uint32, POINTER(FfnSaved), P, P, I,
+    "bdetr_ffn_block_fwd": (c_int, [I, I, P, POINTER(FfnParams), F, c_uint32, P, F, P, POINTER(FfnSaved), P]),
+    "bdetr_ffn_block_bwd": (c_int, [I, I, P, POINTER(FfnParams), F, c_uint32, P, POINTER(FfnSaved), P, P, I,
                                     POINTER(FfnParams), POINTER(FfnScratch), P]),
     "bdetr_add_positional_fwd": (c_int, [I, I, I, P, P, P, P]),
     "bdetr_add_positional_bwd": (c_int, [I, I, I, P, P, P]),
@@ -76,7 +76,7 @@ PROTOTYPES = {
     "bdetr_debug_set_timeline": (c_int, [P]),
     "bdetr_debug_force_attention_kernel": (c_int, [I]),
     "bdetr_head_fwd": (c_int, [I, I, I, I, I, I, F, P, POINTER(HeadParams), F, F, P, I, POINTER(HeadSaved), P]),
-    "bdetr_head_bwd": (c_int, [I, I, I, I, I, F, P, POINTER(HeadParams), F, POINTER(HeadSaved), P, P, I,
+    "bdetr_head_bwd": (c_int, [I, I, I, I, I, I, F, P, POINTER(HeadParams), F, POINTER(HeadSaved), P, P, I,
                                POINTER(HeadParams), POINTER(HeadScratch), P]),
     "bdetr_gemm": (c_int, [I, I, I, P, I, P, I, P, I, I, P, P]),
 }

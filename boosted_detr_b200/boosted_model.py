@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .device import empty, f32, i32, ptr, require_cuda, stream_ptr, zeros
-from .layers import Layer, dropout_key
+from .layers import Layer, dropout_key, dropout_site_key
 from .losses_and_metrics import MatchingLoss, PreparedTargets, raise_for_status
 from .prediction_heads import BoxPredictionHead, MultiClassPredictionHead, SingleClassPredictionHead
 from .transformers import (DecoderBlock, DecoderBlock_NoSelfAttention, DecoderPrep, ImageEncoderAttention, accumulate)
@@ -172,8 +172,11 @@ class BoostedDETR:
                     o._grads[k].zero_()
 
     # -- inputs --------------------------------------------------------------------------------
-    def _pinned(self, name, x, dtype):
-        """numpy -> persistent pinned staging buffer (counted in self.h2d_bytes)."""
+    def _h2d(self, name, x, dtype, dst=None):
+        """host array -> pinned staging slot -> HBM, async on the current stream (counted in self.h2d_bytes).
+        Each (name, shape) has TWO staging slots used alternately, and a slot is only rewritten after the event recorded
+        behind its previous H2D copy has completed -- the host may run ahead of the device (no sync in the step), and a
+        single slot could be overwritten with batch k+1 while the copy of batch k was still queued."""
         arr = x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
         arr = np.ascontiguousarray(arr, dtype=np.int32 if dtype == "i32" else np.float32)
         stage = getattr(self, "_staging", None)
@@ -181,16 +184,31 @@ class BoostedDETR:
             stage = self._staging = {}
         key = (name, arr.shape)
         if key not in stage:
-            stage[key] = torch.empty(arr.shape, dtype=torch.int32 if dtype == "i32" else torch.float32).pin_memory()
-        stage[key].numpy()[...] = arr
+            tdt = torch.int32 if dtype == "i32" else torch.float32
+            stage[key] = {"buf": [torch.empty(arr.shape, dtype=tdt).pin_memory() for _ in range(2)],
+                          "ev": [None, None], "next": 0}
+        st = stage[key]
+        slot = st["next"]
+        st["next"] = slot ^ 1
+        if st["ev"][slot] is not None:
+            st["ev"][slot].synchronize()                       # the copy that last read this slot has run
+        st["buf"][slot].numpy()[...] = arr
         self.h2d_bytes += arr.nbytes
-        return stage[key]
+        if dst is None:
+            out = st["buf"][slot].to(require_cuda(), non_blocking=True)
+        else:
+            dst.copy_(st["buf"][slot].reshape(dst.shape), non_blocking=True)
+            out = dst
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        st["ev"][slot] = ev
+        return out
 
     def _to_device(self, name, x, dtype):
         """host array -> pinned staging -> HBM (async on the current stream); CUDA tensors pass through."""
         if isinstance(x, torch.Tensor) and x.is_cuda:
             return i32(x) if dtype == "i32" else f32(x)
-        return self._pinned(name, x, dtype).to(require_cuda(), non_blocking=True)
+        return self._h2d(name, x, dtype)
 
     def _prepare(self, inputs, training):
         self.h2d_bytes = 0
@@ -204,10 +222,30 @@ class BoostedDETR:
         return feats, y_true
 
     def _keys(self, i):
+        """Per-site halves of the dropout keys of boosted block i.  The step's seed lives in device memory
+        (`_seed_dev`, refreshed by `push_dropout_seed` before every eager step / graph replay) and the kernels combine the
+        two, so a captured graph draws new masks on every replay like Keras Dropout (reference transformers.py:135,147)."""
         if self.dropout_seed is None:
             return None
-        k = lambda s: dropout_key(self.dropout_seed, 8 * i + s)
+        k = lambda s: dropout_site_key(8 * i + s)
         return {"enc": [(k(SITE_ENC_ATTN), k(SITE_ENC_FFN))], "dec": (k(SITE_DEC_SELF), k(SITE_DEC_CROSS), k(SITE_DEC_FFN))}
+
+    def push_dropout_seed(self):
+        """Queues the 4-byte H2D copy of the current `dropout_seed` on the current stream (pinned 16-slot ring: the host
+        may run a few steps ahead of the device)."""
+        if self.dropout_seed is None:
+            return
+        if getattr(self, "_seed_dev", None) is None:
+            self._seed_dev = torch.zeros(1, dtype=torch.int32, device=require_cuda())
+            self._seed_host = torch.zeros(16, dtype=torch.int32).pin_memory()
+            self._seed_slot = 0
+        slot = self._seed_slot = (self._seed_slot + 1) % 16
+        self._seed_host.numpy().view(np.uint32)[slot] = self.dropout_seed & 0xFFFFFFFF
+        self._seed_dev.copy_(self._seed_host[slot:slot + 1], non_blocking=True)
+
+    def advance_dropout_seed(self):
+        if self.dropout_seed is not None:
+            self.dropout_seed = (self.dropout_seed + 1) & 0xFFFFFFFF
 
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
@@ -257,6 +295,9 @@ class BoostedDETR:
         and everything is joined into main before returning."""
         N = self.num_decoder_blocks
         use_dropout = training and self.dropout_seed is not None
+        if use_dropout and not torch.cuda.is_current_stream_capturing():
+            self.push_dropout_seed()
+        seed_dev = self._seed_dev if use_dropout else None
         x = feats
         main = torch.cuda.current_stream()
         side = self._side_stream() if training else None
@@ -296,15 +337,15 @@ class BoostedDETR:
                 aux[2].wait_stream(main)
                 with torch.cuda.stream(aux[2]):
                     dec0 = self.DecoderPrep.tile_queries(x.shape[0], like=x)
-                    pre_self = dec_l.SelfAttentionBlock.forward([dec0, dec0, dec0], training, dkeys[0])
-            (x, pos), c_enc = enc.forward([x], training, keys["enc"] if keys else None)
+                    pre_self = dec_l.SelfAttentionBlock.forward([dec0, dec0, dec0], training, dkeys[0], seed_dev)
+            (x, pos), c_enc = enc.forward([x], training, keys["enc"] if keys else None, seed_dev)
             self._mark(f"fwd enc{i} done (main)")
             dec_s.wait_stream(main)
             with torch.cuda.stream(dec_s):
                 prep_out, c_prep = self.DecoderPrep.forward([x, pos], training, dec=dec0)
                 if pre_self is not None:
                     dec_s.wait_stream(aux[2])
-                dec, c_dec = dec_l.forward(list(prep_out), training, dkeys, pre_self=pre_self)
+                dec, c_dec = dec_l.forward(list(prep_out), training, dkeys, pre_self=pre_self, seed_dev=seed_dev)
                 self._mark(f"fwd dec{i} done (dec)")
                 mult = 2.0 if i == 0 else 1.0                 # block 0 is counted twice (reference :222-229)
                 if cums is not None and training:
@@ -479,8 +520,7 @@ class BoostedDETR:
         if self.optimizer is not None:
             self.optimizer.apply(self)
         self.step_count += 1
-        if self.dropout_seed is not None:
-            self.dropout_seed = (self.dropout_seed + 1) & 0xFFFFFFFF
+        self.advance_dropout_seed()
         if not return_host:
             return m
         return self.host_logs()

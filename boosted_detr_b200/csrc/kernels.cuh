@@ -61,12 +61,13 @@ int launch_attention_bwd_umma(int B, int H, int Lq, int Lk, int d, const float *
 
 // z = resid + dropout(z) (in place), out = LN(z); saves mean/rstd.
 int launch_res_ln_fwd(int M, int D, const float *resid, float *z, const float *gamma, const float *beta, float eps,
-                      float rate, uint32_t key, float *out, float *mean, float *rstd, int round_out, cudaStream_t s);
+                      float rate, uint32_t key, const uint32_t *seed_dev, float *out, float *mean, float *rstd, int round_out,
+                      cudaStream_t s);
 // d_z -> d_resid (overwrite/accumulate) and d_a = dropout'(d_z); g_gamma/g_beta accumulated; g_bias (nullable)
 // accumulates the column sums of d_a = the bias gradient of the Dense layer that produced the LayerNorm input.
 int launch_res_ln_bwd(int M, int D, const float *d_out, const float *z, const float *mean, const float *rstd,
-                      const float *gamma, float rate, uint32_t key, float *d_resid, int acc_resid, float *d_a,
-                      float *g_gamma, float *g_beta, float *g_bias, int round_out, cudaStream_t s);
+                      const float *gamma, float rate, uint32_t key, const uint32_t *seed_dev, float *d_resid, int acc_resid,
+                      float *d_a, float *g_gamma, float *g_beta, float *g_bias, int round_out, cudaStream_t s);
 
 int launch_add_rows_fwd(int B, int L, int D, const float *x, const float *pos, float *out, int round_out, cudaStream_t s);
 int launch_batch_sum_acc(int B, int L, int D, const float *src, float *dst, cudaStream_t s);
@@ -81,7 +82,7 @@ int launch_bn_fwd(int M, int Dh, const float *h, const float *gamma, const float
 // d_h = relu'(h) * BN_backward(d_hn); g_gamma/g_beta accumulated
 int launch_bn_relu_bwd(int M, int Dh, const float *h, const float *d_hn, const float *gamma, const float *mean,
                        const float *rstd, float *acc, float *d_h, float *g_gamma, float *g_beta, float *g_bias, int round_out,
-                       cudaStream_t s);
+                       int batch_stats, cudaStream_t s);
 // act in place on logits [M,N]; cum = (init ? 0 : cum) + mult*act
 int launch_head_act_fwd(int M, int N, int kind, float mult, float *act, float *cum, int cum_init, cudaStream_t s);
 int launch_head_act_bwd(int M, int N, int kind, float mult, const float *act, const float *d_cum, float *d_logits,

@@ -15,9 +15,11 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 res_ln_fwd_kernel(int M, const float *__restrict__ resid, float *__restrict__ z, const float *__restrict__ gamma,
                   const float *__restrict__ beta, float eps, float keep_scale, uint32_t thresh, uint32_t key,
+                  const uint32_t *__restrict__ seed_dev,
                   float *__restrict__ out, float *__restrict__ mean_o, float *__restrict__ rstd_o, int round_out)
 {
     pdl_sync();
+    if (seed_dev) key = lowbias32(*seed_dev ^ key);      // per-step seed read from device memory (CUDA-graph replays)
     constexpr int D = NV * 128;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -63,10 +65,12 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 res_ln_bwd_kernel(int M, const float *__restrict__ d_out, const float *__restrict__ z, const float *__restrict__ mean_i,
                   const float *__restrict__ rstd_i, const float *__restrict__ gamma, float keep_scale, uint32_t thresh,
-                  uint32_t key, float *__restrict__ d_resid, int acc_resid, float *__restrict__ d_a,
-                  float *__restrict__ g_gamma, float *__restrict__ g_beta, float *__restrict__ g_bias, int round_out)
+                  uint32_t key, const uint32_t *__restrict__ seed_dev, float *__restrict__ d_resid, int acc_resid,
+                  float *__restrict__ d_a, float *__restrict__ g_gamma, float *__restrict__ g_beta, float *__restrict__ g_bias,
+                  int round_out)
 {
     pdl_sync();
+    if (seed_dev) key = lowbias32(*seed_dev ^ key);
     constexpr int D = NV * 128;
     __shared__ float red_g[8][D + 4];
     __shared__ float red_b[8][D + 4];
@@ -153,30 +157,31 @@ res_ln_bwd_kernel(int M, const float *__restrict__ d_out, const float *__restric
 }
 
 int launch_res_ln_fwd(int M, int D, const float *resid, float *z, const float *gamma, const float *beta, float eps,
-                      float rate, uint32_t key, float *out, float *mean, float *rstd, int round_out, cudaStream_t s)
+                      float rate, uint32_t key, const uint32_t *seed_dev, float *out, float *mean, float *rstd, int round_out,
+                      cudaStream_t s)
 {
     BDETR_REQUIRE(M > 0 && (D == 128 || D == 256 || D == 512), BDETR_E_UNSUPPORTED, "LayerNorm width must be 128, 256 or 512");
     const uint32_t thresh = dropout_threshold(rate);
     const float ks = 1.0f / (1.0f - rate);
     const int grid = ceil_div(M, 8);
-    if (D == 128) launch_k(res_ln_fwd_kernel<1>, grid, 256, 0, s, M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd, round_out);
-    else if (D == 256) launch_k(res_ln_fwd_kernel<2>, grid, 256, 0, s, M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd, round_out);
-    else launch_k(res_ln_fwd_kernel<4>, grid, 256, 0, s, M, resid, z, gamma, beta, eps, ks, thresh, key, out, mean, rstd, round_out);
+    if (D == 128) launch_k(res_ln_fwd_kernel<1>, grid, 256, 0, s, M, resid, z, gamma, beta, eps, ks, thresh, key, seed_dev, out, mean, rstd, round_out);
+    else if (D == 256) launch_k(res_ln_fwd_kernel<2>, grid, 256, 0, s, M, resid, z, gamma, beta, eps, ks, thresh, key, seed_dev, out, mean, rstd, round_out);
+    else launch_k(res_ln_fwd_kernel<4>, grid, 256, 0, s, M, resid, z, gamma, beta, eps, ks, thresh, key, seed_dev, out, mean, rstd, round_out);
     BDETR_CHECK_LAUNCH("res_ln_fwd_kernel");
     return BDETR_OK;
 }
 
 int launch_res_ln_bwd(int M, int D, const float *d_out, const float *z, const float *mean, const float *rstd,
-                      const float *gamma, float rate, uint32_t key, float *d_resid, int acc_resid, float *d_a,
-                      float *g_gamma, float *g_beta, float *g_bias, int round_out, cudaStream_t s)
+                      const float *gamma, float rate, uint32_t key, const uint32_t *seed_dev, float *d_resid, int acc_resid,
+                      float *d_a, float *g_gamma, float *g_beta, float *g_bias, int round_out, cudaStream_t s)
 {
     BDETR_REQUIRE(M > 0 && (D == 128 || D == 256 || D == 512), BDETR_E_UNSUPPORTED, "LayerNorm width must be 128, 256 or 512");
     const uint32_t thresh = dropout_threshold(rate);
     const float ks = 1.0f / (1.0f - rate);
     const int grid = min(ceil_div(M, 8), 296);
-    if (D == 128) launch_k(res_ln_bwd_kernel<1>, grid, 256, 0, s, M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
-    else if (D == 256) launch_k(res_ln_bwd_kernel<2>, grid, 256, 0, s, M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
-    else launch_k(res_ln_bwd_kernel<4>, grid, 256, 0, s, M, d_out, z, mean, rstd, gamma, ks, thresh, key, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
+    if (D == 128) launch_k(res_ln_bwd_kernel<1>, grid, 256, 0, s, M, d_out, z, mean, rstd, gamma, ks, thresh, key, seed_dev, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
+    else if (D == 256) launch_k(res_ln_bwd_kernel<2>, grid, 256, 0, s, M, d_out, z, mean, rstd, gamma, ks, thresh, key, seed_dev, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
+    else launch_k(res_ln_bwd_kernel<4>, grid, 256, 0, s, M, d_out, z, mean, rstd, gamma, ks, thresh, key, seed_dev, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
     BDETR_CHECK_LAUNCH("res_ln_bwd_kernel");
     return BDETR_OK;
 }
@@ -281,7 +286,8 @@ __device__ __forceinline__ float col_reduce8(float v, float (*red)[33])
 
 constexpr int BN_ROWS = 128;     // rows per CTA: grid = (Dh/32, M/128) so the whole chip takes part
 
-// acc[0:Dh] += sum_m (h - pivot), acc[Dh:2Dh] += sum_m (h - pivot)^2, pivot = h[0, c] (kills the cancellation)
+// per row-chunk partials (no atomics: the forward stays bit-reproducible):
+// acc[chunk][0:Dh] = sum_m (h - pivot), acc[chunk][Dh:2Dh] = sum_m (h - pivot)^2, pivot = h[0, c] (kills the cancellation)
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(int M, int Dh, const float *__restrict__ h, float *__restrict__ acc)
 {
@@ -295,7 +301,7 @@ bn_stats_kernel(int M, int Dh, const float *__restrict__ h, float *__restrict__ 
     if (live) for (int m = m0 + r; m < m1; m += 8) { const float d = h[(size_t)m * Dh + c] - pivot; s1 += d; s2 = fmaf(d, d, s2); }
     s1 = col_reduce8(s1, red);
     s2 = col_reduce8(s2, red);
-    if (live && r == 0) { atomicAdd(&acc[c], s1); atomicAdd(&acc[Dh + c], s2); }
+    if (live && r == 0) { acc[(size_t)blockIdx.y * 2 * Dh + c] = s1; acc[(size_t)blockIdx.y * 2 * Dh + Dh + c] = s2; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -308,7 +314,9 @@ bn_apply_kernel(int M, int Dh, const float *__restrict__ h, const float *__restr
     if (c >= Dh) return;
     float mean, var;
     if (training) {
-        const float a1 = acc[c] / (float)M, a2 = acc[Dh + c] / (float)M;
+        float t1 = 0.0f, t2 = 0.0f;
+        for (int k = 0; k < (int)gridDim.y; ++k) { t1 += acc[(size_t)k * 2 * Dh + c]; t2 += acc[(size_t)k * 2 * Dh + Dh + c]; }   // fixed order
+        const float a1 = t1 / (float)M, a2 = t2 / (float)M;
         mean = h[c] + a1;
         var = fmaxf(a2 - a1 * a1, 0.0f);
         if (blockIdx.y == 0 && r == 0) {
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(256)
 bn_relu_bwd_apply_kernel(int M, int Dh, const float *__restrict__ h, const float *__restrict__ d_hn, const float *__restrict__ gamma,
                          const float *__restrict__ mean_i, const float *__restrict__ rstd_i, const float *__restrict__ acc,
                          float *__restrict__ d_h, float *__restrict__ g_gamma, float *__restrict__ g_beta,
-                         float *__restrict__ g_bias, int round_out)
+                         float *__restrict__ g_bias, int round_out, int batch_stats)
 {
     pdl_sync();
     __shared__ float red[8][33];
@@ -362,8 +370,10 @@ bn_relu_bwd_apply_kernel(int M, int Dh, const float *__restrict__ h, const float
         return;
     }
     const float mean = mean_i[c], rstd = rstd_i[c], g = gamma[c];
-    const float s1 = acc[c], s2 = acc[Dh + c];
-    if (blockIdx.y == 0 && r == 0) { g_gamma[c] += s2; g_beta[c] += s1; }
+    // batch_stats == 0: the layer normalised with its moving statistics (inference mode, or a frozen head: Keras runs a
+    // non-trainable BatchNormalization in inference mode) -- mean / variance are constants, so dx = g * rstd * dy
+    const float s1 = batch_stats ? acc[c] : 0.0f, s2 = batch_stats ? acc[Dh + c] : 0.0f;
+    if (batch_stats && blockIdx.y == 0 && r == 0) { g_gamma[c] += s2; g_beta[c] += s1; }
     const float invM = 1.0f / (float)M;
     const int m0 = blockIdx.y * BN_ROWS, m1 = min(M, m0 + BN_ROWS);
     float bsum = 0.0f;
@@ -389,7 +399,6 @@ int launch_bn_fwd(int M, int Dh, const float *h, const float *gamma, const float
     BDETR_REQUIRE(M > 0 && Dh > 0 && acc, BDETR_E_BAD_SHAPE, "bad BatchNorm arguments");
     dim3 grid(ceil_div(Dh, 32), ceil_div(M, BN_ROWS));
     if (training) {
-        BDETR_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 2 * Dh, s));
         launch_k(bn_stats_kernel, grid, 256, 0, s, M, Dh, h, acc);
         BDETR_CHECK_LAUNCH("bn_stats_kernel");
     }
@@ -399,14 +408,17 @@ int launch_bn_fwd(int M, int Dh, const float *h, const float *gamma, const float
 }
 int launch_bn_relu_bwd(int M, int Dh, const float *h, const float *d_hn, const float *gamma, const float *mean,
                        const float *rstd, float *acc, float *d_h, float *g_gamma, float *g_beta, float *g_bias, int round_out,
-                       cudaStream_t s)
+                       int batch_stats, cudaStream_t s)
 {
     BDETR_REQUIRE(M > 0 && Dh > 0 && acc, BDETR_E_BAD_SHAPE, "bad BatchNorm arguments");
     dim3 grid(ceil_div(Dh, 32), ceil_div(M, BN_ROWS));
-    BDETR_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 2 * Dh, s));
-    launch_k(bn_bwd_stats_kernel, grid, 256, 0, s, M, Dh, h, d_hn, mean, rstd, acc);
-    BDETR_CHECK_LAUNCH("bn_bwd_stats_kernel");
-    launch_k(bn_relu_bwd_apply_kernel, grid, 256, 0, s, M, Dh, h, d_hn, gamma, mean, rstd, acc, d_h, g_gamma, g_beta, g_bias, round_out);
+    if (batch_stats) {
+        BDETR_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 2 * Dh, s));
+        launch_k(bn_bwd_stats_kernel, grid, 256, 0, s, M, Dh, h, d_hn, mean, rstd, acc);
+        BDETR_CHECK_LAUNCH("bn_bwd_stats_kernel");
+    }
+    launch_k(bn_relu_bwd_apply_kernel, grid, 256, 0, s, M, Dh, h, d_hn, gamma, mean, rstd, acc, d_h, g_gamma, g_beta, g_bias, round_out,
+             batch_stats);
     BDETR_CHECK_LAUNCH("bn_relu_bwd_apply_kernel");
     return BDETR_OK;
 }

@@ -40,7 +40,7 @@ API int bdetr_gemm(int M, int N, int K, const float *A, int transA, const float 
 API int bdetr_attention_block_fwd(int B, int Lq, int Lk, int D, int H,
                                   const float *query, const float *key, const float *value,
                                   const bdetr_attn_params *w, float dropout_rate, uint32_t dropout_key,
-                                  float ln_eps, float *out, const bdetr_attn_saved *sv, void *stream)
+                                  const uint32_t *dropout_seed_dev, float ln_eps, float *out, const bdetr_attn_saved *sv, void *stream)
 {
     BDETR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && D > 0 && H > 0 && D % H == 0, BDETR_E_BAD_SHAPE, "bad shape");
     BDETR_REQUIRE(query && key && value && w && out && sv, BDETR_E_NULL, "null pointer");
@@ -58,7 +58,7 @@ API int bdetr_attention_block_fwd(int B, int Lq, int Lk, int D, int H,
     TRY(launch_attention_fwd(B, H, Lq, Lk, D / H, sv->qp, sv->kp, sv->vp, sv->o, sv->lse, rnd, s));
     // sv->o is [B,H,Lq,d]; read back as [B*Lq, D] with no permute (reference transformers.py:100)
     TRY(linear_fwd(Mq, D, D, sv->o, w->wo, w->bo, 0, sv->z, 0, s));
-    TRY(launch_res_ln_fwd(Mq, D, query, sv->z, w->ln_gamma, w->ln_beta, ln_eps, dropout_rate, dropout_key, out, sv->mean, sv->rstd, rnd, s));
+    TRY(launch_res_ln_fwd(Mq, D, query, sv->z, w->ln_gamma, w->ln_beta, ln_eps, dropout_rate, dropout_key, dropout_seed_dev, out, sv->mean, sv->rstd, rnd, s));
     return BDETR_OK;
 }
 
@@ -72,7 +72,7 @@ API int bdetr_attention_core_fwd(int B, int H, int Lq, int Lk, int d, const floa
 API int bdetr_attention_block_bwd(int B, int Lq, int Lk, int D, int H,
                                   const float *query, const float *key, const float *value,
                                   const bdetr_attn_params *w, float dropout_rate, uint32_t dropout_key,
-                                  const bdetr_attn_saved *sv, const float *d_out,
+                                  const uint32_t *dropout_seed_dev, const bdetr_attn_saved *sv, const float *d_out,
                                   float *d_query, float *d_key, float *d_value, int acc_flags,
                                   const bdetr_attn_params *gw, const bdetr_attn_scratch *sc, void *stream)
 {
@@ -83,7 +83,7 @@ API int bdetr_attention_block_bwd(int B, int Lq, int Lk, int D, int H,
     const int Mq = B * Lq, Mk = B * Lk;
     // LayerNorm + residual + dropout: residual gradient goes straight to d_query
     const int rnd = tc_mode();
-    TRY(launch_res_ln_bwd(Mq, D, d_out, sv->z, sv->mean, sv->rstd, w->ln_gamma, dropout_rate, dropout_key,
+    TRY(launch_res_ln_bwd(Mq, D, d_out, sv->z, sv->mean, sv->rstd, w->ln_gamma, dropout_rate, dropout_key, dropout_seed_dev,
                           d_query, acc_flags & 1, sc->d_z, gw->ln_gamma, gw->ln_beta, gw->bo, rnd, s));
     // output projection (its bias gradient was fused into the LayerNorm backward above): the weight half runs
     // beside the data path.  d_o feeds the tcgen05 attention backward MMAs in tensor-core mode: stored tf32-rounded
@@ -104,7 +104,7 @@ API int bdetr_attention_block_bwd(int B, int Lq, int Lk, int D, int H,
 }
 
 API int bdetr_ffn_block_fwd(int M, int D, const float *x, const bdetr_ffn_params *w,
-                            float dropout_rate, uint32_t dropout_key, float ln_eps,
+                            float dropout_rate, uint32_t dropout_key, const uint32_t *dropout_seed_dev, float ln_eps,
                             float *out, const bdetr_ffn_saved *sv, void *stream)
 {
     BDETR_REQUIRE(M > 0 && D > 0, BDETR_E_BAD_SHAPE, "bad shape");
@@ -113,12 +113,12 @@ API int bdetr_ffn_block_fwd(int M, int D, const float *x, const bdetr_ffn_params
     const int rnd = tc_mode();
     TRY(linear_fwd(M, D, D, x, w->w1, w->b1, 1, sv->h, rnd, s));
     TRY(linear_fwd(M, D, D, sv->h, w->w2, w->b2, 0, sv->z, 0, s));
-    TRY(launch_res_ln_fwd(M, D, x, sv->z, w->ln_gamma, w->ln_beta, ln_eps, dropout_rate, dropout_key, out, sv->mean, sv->rstd, rnd, s));
+    TRY(launch_res_ln_fwd(M, D, x, sv->z, w->ln_gamma, w->ln_beta, ln_eps, dropout_rate, dropout_key, dropout_seed_dev, out, sv->mean, sv->rstd, rnd, s));
     return BDETR_OK;
 }
 
 API int bdetr_ffn_block_bwd(int M, int D, const float *x, const bdetr_ffn_params *w,
-                            float dropout_rate, uint32_t dropout_key,
+                            float dropout_rate, uint32_t dropout_key, const uint32_t *dropout_seed_dev,
                             const bdetr_ffn_saved *sv, const float *d_out,
                             float *d_x, int accumulate_dx,
                             const bdetr_ffn_params *gw, const bdetr_ffn_scratch *sc, void *stream)
@@ -127,7 +127,7 @@ API int bdetr_ffn_block_bwd(int M, int D, const float *x, const bdetr_ffn_params
     BDETR_REQUIRE(x && w && sv && d_out && d_x && gw && sc && sc->d_z && sc->d_h, BDETR_E_NULL, "null pointer");
     cudaStream_t s = as_stream(stream);
     const int rnd = tc_mode();
-    TRY(launch_res_ln_bwd(M, D, d_out, sv->z, sv->mean, sv->rstd, w->ln_gamma, dropout_rate, dropout_key,
+    TRY(launch_res_ln_bwd(M, D, d_out, sv->z, sv->mean, sv->rstd, w->ln_gamma, dropout_rate, dropout_key, dropout_seed_dev,
                           d_x, accumulate_dx, sc->d_z, gw->ln_gamma, gw->ln_beta, gw->b2, rnd, s));
     // DenseLinear (bias gradient fused above), then ReLU mask on the way into DenseRelu; weight halves run beside
     Branches br(s);
@@ -190,7 +190,7 @@ API int bdetr_head_fwd(int M, int D, int Dh, int Nout, int kind, int training, f
     return BDETR_OK;
 }
 
-API int bdetr_head_bwd(int M, int D, int Dh, int Nout, int kind, float mult,
+API int bdetr_head_bwd(int M, int D, int Dh, int Nout, int kind, int bn_training, float mult,
                        const float *x, const bdetr_head_params *w, float bn_eps,
                        const bdetr_head_saved *sv, const float *d_cum,
                        float *d_x, int accumulate_dx,
@@ -205,7 +205,7 @@ API int bdetr_head_bwd(int M, int D, int Dh, int Nout, int kind, float mult,
     TRY(linear_wgrad(M, Nout, Dh, sv->hn, sc->d_logits, gw->w2, gw->b2, br.fork(0)));
     TRY(linear_dgrad(M, Nout, Dh, w->w2, sc->d_logits, sc->d_hn, 0, nullptr, 0, s));
     TRY(launch_bn_relu_bwd(M, Dh, sv->h, sc->d_hn, w->bn_gamma, sv->bn_mean, sv->bn_rstd, sv->bn_acc, sc->d_h, gw->bn_gamma,
-                           gw->bn_beta, gw->b1, tc_mode(), s));
+                           gw->bn_beta, gw->b1, tc_mode(), bn_training, s));
     TRY(linear_wgrad(M, Dh, D, x, sc->d_h, gw->w1, nullptr, br.fork(1)));
     TRY(linear_dgrad(M, Dh, D, w->w1, sc->d_h, d_x, accumulate_dx, nullptr, 0, s));
     return br.join();

@@ -71,18 +71,20 @@ class GraphedTrainStep:
                 dst.copy_(x.reshape(dst.shape), non_blocking=True)       # already in pinned host memory: no staging copy
                 m.h2d_bytes += x.numel() * x.element_size()
             else:
-                dst.copy_(m._pinned(k, x, dtype).reshape(dst.shape), non_blocking=True)
+                m._h2d(k, x, dtype, dst=dst)
 
     def replay(self):
         m = self.model
         if self.optimizer_in_graph:
             m.optimizer.pre_replay()
+        m.push_dropout_seed()                     # this step's dropout seed -> the device word the captured kernels read
         self.graph.replay()
         if m.grad_allreduce is not None and m.grad_bucket_hook is None:
             m.grad_allreduce(m._flat[1])          # non-overlapped mode: one all-reduce after the graph
         if m.optimizer is not None and not self.optimizer_in_graph:
             m.optimizer.apply(m)
         m.step_count += 1
+        m.advance_dropout_seed()
 
     # -- input prefetch (opt-in; NOT yet validated on the GPU: see DESIGN.md §7) -------------------------------------
     def prefetch(self, inputs):
@@ -101,8 +103,9 @@ class GraphedTrainStep:
             for k, dst in self._staging.items():
                 x = inputs[k]
                 if not (isinstance(x, torch.Tensor) and (x.is_cuda or x.is_pinned())):
-                    x = self.model._pinned(k, x, "i32" if k == "num_objects" else "f32")
-                dst.copy_(x.reshape(dst.shape), non_blocking=True)
+                    self.model._h2d(k, x, "i32" if k == "num_objects" else "f32", dst=dst)
+                else:
+                    dst.copy_(x.reshape(dst.shape), non_blocking=True)
             self._staged_ev.record(cs)
         self._staged_for = inputs
 

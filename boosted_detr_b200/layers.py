@@ -23,9 +23,14 @@ def lowbias32(x: int) -> int:
     return x
 
 
+def dropout_site_key(site: int) -> int:
+    """Seed-independent half of the key: what the kernels combine with the device-resident step seed."""
+    return lowbias32((site + 0x9E3779B9) & 0xFFFFFFFF)
+
+
 def dropout_key(seed: int, site: int) -> int:
     """Key of the counter-based dropout mask of one Dropout layer instance (DESIGN.md "dropout")."""
-    return lowbias32((seed & 0xFFFFFFFF) ^ lowbias32((site + 0x9E3779B9) & 0xFFFFFFFF))
+    return lowbias32((seed & 0xFFFFFFFF) ^ dropout_site_key(site))
 
 
 def truncated_normal(rng: np.random.Generator, shape, stddev: float) -> np.ndarray:

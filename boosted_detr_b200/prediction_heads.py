@@ -68,16 +68,20 @@ class _Head(Layer):
                              "Conv1D re-projection of the prediction axis is not on the supported path")
         M = x.shape[0] * x.shape[1]
         Dh, N = self.hidden_dim, self.num_out
-        sv = {"h": empty(M, Dh), "hn": empty(M, Dh), "bn_mean": empty(Dh), "bn_rstd": empty(Dh), "bn_acc": empty(2 * Dh),
+        sv = {"h": empty(M, Dh), "hn": empty(M, Dh), "bn_mean": empty(Dh), "bn_rstd": empty(Dh), "bn_acc": empty(2 * Dh * ((M + 127) // 128)),
               "act": empty(x.shape[0], x.shape[1], N)}
         init = cum is None
         if init:
             cum = empty(x.shape[0], x.shape[1], N)
         w, _ = self._structs()
         svs = _struct(_lib.HeadSaved, sv)
-        _lib.call("bdetr_head_fwd", M, D, Dh, N, self.kind, 1 if training else 0, float(mult), ptr(x), ctypes.byref(w),
+        # Keras: a BatchNormalization whose layer is frozen (trainable = False, reference notebook cell 30) runs in
+        # inference mode -- moving statistics, no update -- even inside a training step
+        bn_training = 1 if (training and self.trainable) else 0
+        _lib.call("bdetr_head_fwd", M, D, Dh, N, self.kind, bn_training, float(mult), ptr(x), ctypes.byref(w),
                   BN_EPS, BN_MOMENTUM, ptr(cum), 1 if init else 0, ctypes.byref(svs), stream_ptr())
-        ctx = {"x": x, "saved": sv, "saved_struct": svs, "dims": (M, D, Dh, N), "mult": float(mult), "cum": cum}
+        ctx = {"x": x, "saved": sv, "saved_struct": svs, "dims": (M, D, Dh, N), "mult": float(mult), "cum": cum,
+               "bn_training": bn_training}
         return sv["act"], ctx
 
     def backward(self, ctx, d_cum, d_x=None, acc=False):
@@ -88,7 +92,7 @@ class _Head(Layer):
         sc = {"d_logits": empty(M, N), "d_hn": empty(M, Dh), "d_h": empty(M, Dh)}
         w, gw = self._structs()
         scs = _struct(_lib.HeadScratch, sc)
-        _lib.call("bdetr_head_bwd", M, D, Dh, N, self.kind, ctx["mult"], ptr(ctx["x"]), ctypes.byref(w), BN_EPS,
+        _lib.call("bdetr_head_bwd", M, D, Dh, N, self.kind, ctx["bn_training"], ctx["mult"], ptr(ctx["x"]), ctypes.byref(w), BN_EPS,
                   ctypes.byref(ctx["saved_struct"]), ptr(f32(d_cum)), ptr(d_x), 1 if acc else 0, ctypes.byref(gw),
                   ctypes.byref(scs), stream_ptr())
         return d_x

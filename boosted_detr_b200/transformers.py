@@ -84,7 +84,9 @@ class AttentionBlock(Layer):
             self._struct_cache = (pack(wa, self._weights), pack(a._grads, self._grads), mode)
         return self._struct_cache[:2]
 
-    def forward(self, inputs, training=False, dropout_key=0):
+    def forward(self, inputs, training=False, dropout_key=0, seed_dev=None):
+        """`seed_dev` (optional device uint32 word): the kernels then derive the mask key as
+        lowbias32(*seed_dev ^ dropout_key), so a captured CUDA graph draws a fresh mask per replay."""
         query, key, value = (f32(t) for t in inputs)
         self.maybe_build([query, key, value])
         B, Lq, D = query.shape
@@ -96,9 +98,9 @@ class AttentionBlock(Layer):
         w, _ = self._structs()
         svs = _struct(_lib.AttnSaved, sv)
         _lib.call("bdetr_attention_block_fwd", B, Lq, Lk, D, H, ptr(query), ptr(key), ptr(value), ctypes.byref(w),
-                  rate, dropout_key, LN_EPS, ptr(out), ctypes.byref(svs), stream_ptr())
+                  rate, dropout_key, ptr(seed_dev), LN_EPS, ptr(out), ctypes.byref(svs), stream_ptr())
         ctx = {"inputs": (query, key, value), "saved": sv, "saved_struct": svs, "rate": rate, "key": dropout_key,
-               "dims": (B, Lq, Lk, D, H)}
+               "seed_dev": seed_dev, "dims": (B, Lq, Lk, D, H)}
         return out, ctx
 
     def backward(self, ctx, d_out, d_query=None, d_key=None, d_value=None, acc=(False, False, False)):
@@ -127,7 +129,7 @@ class AttentionBlock(Layer):
         scs = _struct(_lib.AttnScratch, sc)
         flags = (1 if acc[0] else 0) | (2 if acc[1] else 0) | (4 if acc[2] else 0)
         _lib.call("bdetr_attention_block_bwd", B, Lq, Lk, D, H, ptr(query), ptr(key), ptr(value), ctypes.byref(w),
-                  ctx["rate"], ctx["key"], ctypes.byref(ctx["saved_struct"]), ptr(f32(d_out)),
+                  ctx["rate"], ctx["key"], ptr(ctx["seed_dev"]), ctypes.byref(ctx["saved_struct"]), ptr(f32(d_out)),
                   ptr(d_query), ptr(d_key), ptr(d_value), flags, ctypes.byref(gw), ctypes.byref(scs), stream_ptr())
         return d_query, d_key, d_value
 
@@ -158,7 +160,7 @@ class FeedForwardBlock(Layer):
             self._struct_cache = (pack(w), pack(self._grads), mode)
         return self._struct_cache[:2]
 
-    def forward(self, inputs, training=False, dropout_key=0):
+    def forward(self, inputs, training=False, dropout_key=0, seed_dev=None):
         x = f32(inputs[0])
         self.maybe_build([x])
         D = x.shape[-1]
@@ -168,9 +170,10 @@ class FeedForwardBlock(Layer):
         rate = self.rate if training else 0.0
         w, _ = self._structs()
         svs = _struct(_lib.FfnSaved, sv)
-        _lib.call("bdetr_ffn_block_fwd", M, D, ptr(x), ctypes.byref(w), rate, dropout_key, LN_EPS, ptr(out),
-                  ctypes.byref(svs), stream_ptr())
-        return out, {"x": x, "saved": sv, "saved_struct": svs, "rate": rate, "key": dropout_key, "dims": (M, D)}
+        _lib.call("bdetr_ffn_block_fwd", M, D, ptr(x), ctypes.byref(w), rate, dropout_key, ptr(seed_dev), LN_EPS,
+                  ptr(out), ctypes.byref(svs), stream_ptr())
+        return out, {"x": x, "saved": sv, "saved_struct": svs, "rate": rate, "key": dropout_key, "seed_dev": seed_dev,
+                     "dims": (M, D)}
 
     def backward(self, ctx, d_out, d_x=None, acc=False):
         M, D = ctx["dims"]
@@ -180,7 +183,7 @@ class FeedForwardBlock(Layer):
         w, gw = self._structs()
         scs = _struct(_lib.FfnScratch, sc)
         _lib.call("bdetr_ffn_block_bwd", M, D, ptr(ctx["x"]), ctypes.byref(w), ctx["rate"], ctx["key"],
-                  ctypes.byref(ctx["saved_struct"]), ptr(f32(d_out)), ptr(d_x), 1 if acc else 0, ctypes.byref(gw),
+                  ptr(ctx["seed_dev"]), ctypes.byref(ctx["saved_struct"]), ptr(f32(d_out)), ptr(d_x), 1 if acc else 0, ctypes.byref(gw),
                   ctypes.byref(scs), stream_ptr())
         return d_x
 
@@ -217,12 +220,12 @@ class EncoderBlock(Layer):
     def get_config(self):
         return {**super().get_config(), "num_attention_heads": self.num_attention_heads}
 
-    def forward(self, inputs, training=False, dropout_keys=(0, 0)):
+    def forward(self, inputs, training=False, dropout_keys=(0, 0), seed_dev=None):
         x, pos = inputs
         x = f32(x)
         xp = add_positional(x, pos)                                   # Add1 == Add2 (:226-227)
-        a, c1 = self.SelfAttentionBlock.forward([xp, xp, x], training, dropout_keys[0])
-        y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[1])
+        a, c1 = self.SelfAttentionBlock.forward([xp, xp, x], training, dropout_keys[0], seed_dev)
+        y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[1], seed_dev)
         return y, {"attn": c1, "ffn": c2}
 
     def backward(self, ctx, d_out, d_pos):
@@ -264,7 +267,7 @@ class ImageEncoderAttention(Layer):
         _, R, Cc, D = input_shape[0]
         self.add_weight("positional_encoding", positional_table(R, Cc, D))
 
-    def forward(self, inputs, training=False, dropout_keys=None):
+    def forward(self, inputs, training=False, dropout_keys=None, seed_dev=None):
         x4 = f32(inputs[0])
         self.maybe_build([x4])
         B, R, Cc, D = x4.shape
@@ -273,7 +276,7 @@ class ImageEncoderAttention(Layer):
         ctxs = []
         for i, blk in enumerate(self.EncoderBlocks):
             keys = (0, 0) if dropout_keys is None else dropout_keys[i]
-            x, c = blk.forward([x, pos.view(R * Cc, D)], training, keys)
+            x, c = blk.forward([x, pos.view(R * Cc, D)], training, keys, seed_dev)
             ctxs.append(c)
         return (x.view(B, R, Cc, D), pos), {"blocks": ctxs, "shape": (B, R, Cc, D)}
 
@@ -351,10 +354,10 @@ class DecoderBlock_NoSelfAttention(Layer):
     def get_config(self):
         return {**super().get_config(), "num_attention_heads": self.num_attention_heads}
 
-    def forward(self, inputs, training=False, dropout_keys=(0, 0, 0), pre_self=None):
+    def forward(self, inputs, training=False, dropout_keys=(0, 0, 0), pre_self=None, seed_dev=None):
         enc_value, dec, enc_key, _ = inputs
-        a, c1 = self.JointAttentionBlock.forward([dec, enc_key, enc_value], training, dropout_keys[1])
-        y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[2])
+        a, c1 = self.JointAttentionBlock.forward([dec, enc_key, enc_value], training, dropout_keys[1], seed_dev)
+        y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[2], seed_dev)
         return y, {"joint": c1, "ffn": c2}
 
     def backward(self, ctx, d_out, defer_self=False):
@@ -380,13 +383,13 @@ class DecoderBlock(Layer):
     def get_config(self):
         return {**super().get_config(), "num_attention_heads": self.num_attention_heads}
 
-    def forward(self, inputs, training=False, dropout_keys=(0, 0, 0), pre_self=None):
+    def forward(self, inputs, training=False, dropout_keys=(0, 0, 0), pre_self=None, seed_dev=None):
         """pre_self: (output, ctx) of SelfAttentionBlock.forward([dec, dec, dec]) when the caller already ran it
         (it depends on the queries only, so the model overlaps it with the encoder block)."""
         enc_value, dec, enc_key, _ = inputs
-        s, c0 = pre_self if pre_self is not None else self.SelfAttentionBlock.forward([dec, dec, dec], training, dropout_keys[0])
-        a, c1 = self.JointAttentionBlock.forward([s, enc_key, enc_value], training, dropout_keys[1])
-        y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[2])
+        s, c0 = pre_self if pre_self is not None else self.SelfAttentionBlock.forward([dec, dec, dec], training, dropout_keys[0], seed_dev)
+        a, c1 = self.JointAttentionBlock.forward([s, enc_key, enc_value], training, dropout_keys[1], seed_dev)
+        y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[2], seed_dev)
         return y, {"self": c0, "joint": c1, "ffn": c2}
 
     def backward(self, ctx, d_out, defer_self=False):

@@ -156,11 +156,15 @@ typedef struct {
  *   out = LayerNorm_eps( query + Dropout( MHA(query,key,value) ) )
  * query [B,Lq,D] (also the residual), key/value [B,Lk,D]; H heads of width D/H; the attention
  * output is re-read as [B,Lq,D] WITHOUT permuting back (reference line :100).
- * dropout_rate 0 disables dropout (inference); the keep mask is hash(idx ^ dropout_key). */
+ * dropout_rate 0 disables dropout (inference); the keep mask is hash(idx ^ key) >= rate * 2^32 with
+ * key = dropout_key when dropout_seed_dev is NULL, else key = lowbias32(*dropout_seed_dev ^ dropout_key): the
+ * per-step seed is then read from DEVICE memory by the kernels, so a captured CUDA graph draws a fresh mask on every
+ * replay (Keras Dropout semantics, reference transformers.py:135,147) once the caller refreshes that word. */
 int bdetr_attention_block_fwd(int B, int Lq, int Lk, int D, int H,
                               const float *query, const float *key, const float *value,
                               const bdetr_attn_params *w, float dropout_rate, uint32_t dropout_key,
-                              float ln_eps, float *out, const bdetr_attn_saved *saved, void *stream);
+                              const uint32_t *dropout_seed_dev, float ln_eps, float *out,
+                              const bdetr_attn_saved *saved, void *stream);
 
 /* The attention core alone (transformers.py:77-97): qp [B,Lq,H*d], kp/vp [B,Lk,H*d] are the projected tensors
  * (head = d-column slice), o [B,H,Lq,d], lse [B,H,Lq] (log2 units).  Scores are never written to HBM.
@@ -174,7 +178,7 @@ int bdetr_attention_core_fwd(int B, int H, int Lq, int Lk, int d, const float *q
 int bdetr_attention_block_bwd(int B, int Lq, int Lk, int D, int H,
                               const float *query, const float *key, const float *value,
                               const bdetr_attn_params *w, float dropout_rate, uint32_t dropout_key,
-                              const bdetr_attn_saved *saved, const float *d_out,
+                              const uint32_t *dropout_seed_dev, const bdetr_attn_saved *saved, const float *d_out,
                               float *d_query, float *d_key, float *d_value, int acc_flags,
                               const bdetr_attn_params *gw, const bdetr_attn_scratch *scratch,
                               void *stream);
@@ -196,10 +200,10 @@ typedef struct {
 
 /* FeedForwardBlock.call (transformers.py:182-193): out = LN( x + Dropout( relu(xW1+b1)W2+b2 ) ). */
 int bdetr_ffn_block_fwd(int M, int D, const float *x, const bdetr_ffn_params *w,
-                        float dropout_rate, uint32_t dropout_key, float ln_eps,
+                        float dropout_rate, uint32_t dropout_key, const uint32_t *dropout_seed_dev, float ln_eps,
                         float *out, const bdetr_ffn_saved *saved, void *stream);
 int bdetr_ffn_block_bwd(int M, int D, const float *x, const bdetr_ffn_params *w,
-                        float dropout_rate, uint32_t dropout_key,
+                        float dropout_rate, uint32_t dropout_key, const uint32_t *dropout_seed_dev,
                         const bdetr_ffn_saved *saved, const float *d_out,
                         float *d_x, int accumulate_dx,
                         const bdetr_ffn_params *gw, const bdetr_ffn_scratch *scratch, void *stream);
@@ -234,7 +238,7 @@ typedef struct {
     float *h;                /* [M,Dh] relu(x W1 + b1)               */
     float *hn;               /* [M,Dh] batch-normalised              */
     float *bn_mean, *bn_rstd;/* [Dh]                                 */
-    float *bn_acc;           /* [2*Dh] scratch for cross-CTA column sums */
+    float *bn_acc;           /* [2*Dh*ceil(M/128)] scratch for the per-row-chunk column sums */
     float *act;              /* [M,Nout] post-activation output      */
 } bdetr_head_saved;
 
@@ -247,8 +251,10 @@ typedef struct {
 int bdetr_head_fwd(int M, int D, int Dh, int Nout, int kind, int training, float mult,
                    const float *x, const bdetr_head_params *w, float bn_eps, float bn_momentum,
                    float *cum, int cum_init, const bdetr_head_saved *saved, void *stream);
-/* d_cum [M,Nout] is the gradient w.r.t. the running prediction this head was added into. */
-int bdetr_head_bwd(int M, int D, int Dh, int Nout, int kind, float mult,
+/* d_cum [M,Nout] is the gradient w.r.t. the running prediction this head was added into.  bn_training must equal the
+ * `training` flag of the forward call: 0 = the BatchNorm used its moving statistics (inference, or a frozen head -- a
+ * non-trainable Keras BatchNormalization runs in inference mode), so they are constants in the backward. */
+int bdetr_head_bwd(int M, int D, int Dh, int Nout, int kind, int bn_training, float mult,
                    const float *x, const bdetr_head_params *w, float bn_eps,
                    const bdetr_head_saved *saved, const float *d_cum,
                    float *d_x, int accumulate_dx,

@@ -123,6 +123,9 @@ def batch_norm(x, p, prefix, training, new_stats=None):
 # ----------------------------------------------------------------------------------------
 # transformers.py
 # ----------------------------------------------------------------------------------------
+ATTENTION_QUERY_CHUNK = 0      # bench.py's config-5 CPU leg sets this (query rows per slice); 0 = the reference's one-shot form
+
+
 def multihead_attention(query, key, value, p, prefix, num_heads):
     """MultiheadAttention.call, transformers.py:68-102 (mask is always ones on this path)."""
     B, Lq, _ = query.shape
@@ -135,10 +138,16 @@ def multihead_attention(query, key, value, p, prefix, num_heads):
     q = q.reshape(B, Lq, num_heads, d).permute(0, 2, 1, 3)      # :77,82  [B,H,Lq,d]
     k = k.reshape(B, Lk, num_heads, d).permute(0, 2, 3, 1)      # :78,83  [B,H,d,Lk]
     v = v.reshape(B, Lk, num_heads, d).permute(0, 2, 1, 3)      # :79,84  [B,H,Lk,d]
-    x = q @ k                                                   # :87
-    x = x * (1.0 / math.sqrt(float(d)))                         # :88 Rescaling(scale=1/sqrt(dim))
-    x = torch.softmax(x, dim=-1)                                # :89
-    x = x @ v                                                   # :97  [B,H,Lq,d]
+    if ATTENTION_QUERY_CHUNK and Lq > ATTENTION_QUERY_CHUNK:
+        # identical arithmetic row by row (every softmax row still sees all Lk keys); only bounds the host memory the
+        # [B,H,Lq,Lk] score tensor needs at BASELINE config 5's 20 020-token sequences (51 GB otherwise)
+        x = torch.cat([torch.softmax((q[:, :, i:i + ATTENTION_QUERY_CHUNK] @ k) * (1.0 / math.sqrt(float(d))), dim=-1) @ v
+                       for i in range(0, Lq, ATTENTION_QUERY_CHUNK)], dim=2)
+    else:
+        x = q @ k                                               # :87
+        x = x * (1.0 / math.sqrt(float(d)))                     # :88 Rescaling(scale=1/sqrt(dim))
+        x = torch.softmax(x, dim=-1)                            # :89
+        x = x @ v                                               # :97  [B,H,Lq,d]
     x = x.contiguous().reshape(B, Lq, hd)                       # :100 raw reshape, NO permute back (Q1)
     return dense(x, p, prefix + "/OutputProjection")            # :101
 
@@ -399,7 +408,7 @@ def model_weights(attribute_weight=1.0, classification_only=False):
 
 
 def boosted_detr_call(p, features, targets, num_blocks, num_heads, training,
-                      drop=None, weights=None, new_stats=None, forced_masks=None):
+                      drop=None, weights=None, new_stats=None, forced_masks=None, frozen_blocks=()):
     """BoostedDETR.call :170-267 starting at the BackboneNeck output `features` [B,R,Cc,D].
 
     targets = (category one-hot [B,T,C], attribute multi-hot [B,T,A], bbox [B,T,4], num_objects [B])
@@ -419,9 +428,13 @@ def boosted_detr_call(p, features, targets, num_blocks, num_heads, training,
         enc_value, dec, enc_key, _ = decoder_prep(x, pos, p)      # :210
         dec = decoder_block(enc_value, dec, enc_key, p, f"DecoderBlock_{i}", num_heads, drop, i,
                             training, self_attention=(i >= 1))    # :213
-        cat_i = category_head(dec, p, f"CategoryPredictionHead_{i}", training, new_stats)
-        attr_i = attribute_head(dec, p, f"AttributePredictionHead_{i}", training, new_stats)
-        box_i = box_head(dec, p, f"BoxPredictionHead_{i}", training, new_stats)
+        # Keras: BatchNormalization inside a layer with trainable = False (the freezing schedule of
+        # Boosted_DETR_COCO.ipynb cell 30) runs in inference mode -- moving statistics, no update -- even when the
+        # model is called with training=True.  Dropout of frozen blocks still follows `training`.
+        bn_training = training and i not in frozen_blocks
+        cat_i = category_head(dec, p, f"CategoryPredictionHead_{i}", bn_training, new_stats)
+        attr_i = attribute_head(dec, p, f"AttributePredictionHead_{i}", bn_training, new_stats)
+        box_i = box_head(dec, p, f"BoxPredictionHead_{i}", bn_training, new_stats)
         if i == 0:                                                # :222-225
             cat_preds, attr_preds, box_preds = cat_i, attr_i, box_i
         cat_preds = cat_preds + cat_i                             # :227-229 (block 0 twice, Q2)
@@ -460,7 +473,7 @@ def params_to_torch(params: dict, dtype=torch.float64, requires_grad=False) -> d
 
 
 def train_step_reference(params, features, targets, num_blocks, num_heads, dtype=torch.float64,
-                         dropout_seed=None, weights=None, forced_masks=None):
+                         dropout_seed=None, weights=None, forced_masks=None, frozen_blocks=()):
     """Forward (training=True) + gradient of the summed loss vector (Keras train_step semantics:
     tape.gradient of a [B] vector = gradient of its sum).  Returns (out, grads dict, new BN stats)."""
     p = params_to_torch(params, dtype, requires_grad=True)
@@ -469,7 +482,7 @@ def train_step_reference(params, features, targets, num_blocks, num_heads, dtype
           torch.tensor(np.asarray(targets[2]), dtype=dtype), np.asarray(targets[3]))
     new_stats = {}
     out = boosted_detr_call(p, feats, tg, num_blocks, num_heads, True, Dropout(dropout_seed),
-                            weights, new_stats, forced_masks)
+                            weights, new_stats, forced_masks, frozen_blocks)
     out["loss"].sum().backward()
     grads = {k: (v.grad.detach().numpy() if v.grad is not None else np.zeros(v.shape))
              for k, v in p.items() if v.requires_grad}

@@ -1,5 +1,5 @@
 """Per-source-line instruction / stall-sample shares of one kernel from an .ncu-rep captured with --import-source on
-(not a pytest file).  usage: python tests/ncu_lines.py report.ncu-rep kernel_regex [min_pct]"""
+(not a pytest file).  usage: python tools/ncu_lines.py report.ncu-rep kernel_regex [min_pct]"""
 import csv, io, subprocess, sys
 rep, rx = sys.argv[1], sys.argv[2]
 min_pct = float(sys.argv[3]) if len(sys.argv) > 3 else 0.5

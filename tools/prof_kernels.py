@@ -2,7 +2,7 @@
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from util import synth_preds, synth_targets
 from boosted_detr_b200 import _lib
 from boosted_detr_b200.device import ptr, stream_ptr

@@ -1,5 +1,5 @@
 """Reduces an .ncu-rep (ncu --set full) to the handful of per-launch metrics quoted in profiles/ (not a pytest file).
-usage: python tests/summarise_ncu.py report.ncu-rep > summary.csv"""
+usage: python tools/summarise_ncu.py report.ncu-rep > summary.csv"""
 import csv, io, subprocess, sys
 KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__waves_per_multiprocessor", "sm__warps_active.avg.pct_of_peak_sustained_active",

@@ -1,6 +1,6 @@
 """Timeline of one CUDA-graph-replayed training step at BASELINE config 2 (not a pytest file): the model drops timing
 events (external event-record nodes) at the end of every phase of every boosted block; printed as milliseconds from
-the start of the step, per stream.  usage: python tests/trace_step.py [tf32|fp32]"""
+the start of the step, per stream.  usage: python tools/trace_step.py [tf32|fp32]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
