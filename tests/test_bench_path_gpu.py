@@ -141,31 +141,59 @@ def test_concurrency_switch_does_not_change_results(tc_mode):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
-def test_step0_identical_queries_give_identity_assignment(mode):
-    """The reference initialises the shared queries to zeros (transformers.py:428-431): at step 0 every query row is
-    identical, every block's predictions are identical across queries, the cost matrix has identical columns and
-    scipy's tie rule assigns target row t to prediction column t.  That only survives if identical rows stay
-    BIT-identical through every kernel of the forward path."""
+def test_step0_zero_queries_tie_structure(mode):
+    """The reference initialises the shared queries to zeros (transformers.py:428-431), so at step 0 every query row
+    enters the decoder identical.  Because the attention output [B,H,Lq,d] is re-read as [B,Lq,H*d] without a permute
+    (quirk Q1, transformers.py:100), output row r is the concatenation of flat rows 8r..8r+7 of the [H*Lq, d] view: rows
+    whose eight pieces come from the same heads stay identical, rows that straddle a head boundary do not -- the
+    predictions fall into a few groups of exactly tied queries (NOT one group: SURVEY 7.2's "identity assignment" claim
+    overlooked Q1).  What parity needs at this step: (1) queries the fp64 oracle ties stay BIT-identical through every
+    kernel (no order-dependent arithmetic between rows), so the ties are real ties; (2) the solver breaks them exactly
+    like scipy does on the same cost bits; (3) in fp32 mode the assignment equals the oracle's."""
+    from scipy.optimize import linear_sum_assignment
     from boosted_detr_b200 import _lib
     from boosted_detr_b200.boosted_model import BoostedDETR
     from boosted_detr_b200.parameters import baseline_params
+    from oracle import reference_path as R
     lib = _lib.load()
     lib.bdetr_set_mode(_lib.MODE_TF32 if mode == "tf32" else _lib.MODE_FP32)
     try:
+        N = 2
         model = BoostedDETR(**baseline_params(1), attribute_weight=1.0, seed=0).build()
         model.dropout_seed = None                       # dropout masks differ per row: off for this check
-        assert float(np.abs(model.get_weights_dict()["DecoderPrep/init_decoder_features"]).max()) == 0.0
+        w = model.get_weights_dict()
+        assert float(np.abs(w["DecoderPrep/init_decoder_features"]).max()) == 0.0
         rng = np.random.default_rng(5)
-        B, T = 4, 20
+        B, T, Q = 4, 20, 100
         cat, attr, box, n = synth_targets(rng, B, T, model.num_categories, model.num_attributes)
         feats = np.tanh(rng.standard_normal((B, 20, 20, 256))).astype(np.float32)
         model.train_step({"features": feats, "category": cat, "attribute": attr, "bbox": box, "num_objects": n})
+        out, _, _ = R.train_step_reference(w, feats, (cat, attr, box, n), N, 8, torch.float64, weights=R.model_weights(1.0))
+        groups_seen = 0
         for i, c in enumerate(model.last_ctx_train["loss"]):
+            ref_cat = out["per_block_preds"][i][0].detach().numpy()              # [B,Q,C] fp64
+            got = [p.cpu().numpy() for p in c["pred"]]
             cost = c["cost"].cpu().numpy()
             c4r = c["col4row"].cpu().numpy()
-            assert (cost == cost[:, :, :1]).all(), f"block {i}: cost columns differ although the queries are identical"
             for b in range(B):
-                assert (c4r[b, :n[b]] == np.arange(n[b])).all(), f"block {i} image {b}: not the identity assignment"
+                # groups of queries the oracle ties (identical rows up to fp64 rounding of the row-independent GEMMs)
+                key = np.round(ref_cat[b] / 1e-11).astype(np.int64)
+                _, inv = np.unique(key, axis=0, return_inverse=True)
+                inv = inv.reshape(-1)
+                for gid in np.unique(inv):
+                    rows = np.nonzero(inv == gid)[0]
+                    if len(rows) < 2:
+                        continue
+                    groups_seen += 1
+                    for arr in got:
+                        assert (arr[b, rows] == arr[b, rows[:1]]).all(), f"block {i} image {b}: tied queries {rows[:4]}.. are not bit-identical"
+                    assert (cost[b][:, rows] == cost[b][:, rows[:1]]).all()
+                r_, c_ = linear_sum_assignment(cost[b, :n[b], :])
+                assert (c4r[b, :n[b]] == c_).all(), f"block {i} image {b}: solver differs from scipy on its own tie-heavy cost matrix"
+                if mode == "fp32":
+                    ref_mask = out["masks"][i][b].numpy()
+                    assert (ref_mask[np.arange(n[b]), c4r[b, :n[b]]] == 1).all(), f"block {i} image {b}: assignment differs from the oracle's"
+        assert groups_seen >= B * N * 4, "expected several groups of tied queries per image at step 0"
     finally:
         lib.bdetr_set_mode(_lib.MODE_FP32)
 
@@ -231,5 +259,5 @@ def test_frozen_head_batchnorm_runs_in_inference_mode():
     assert nerr(model.metric_tensors["loss"].cpu().numpy(), out["loss"].detach().numpy()) < 1e-5
     g = model.get_grads_dict()
     for k, ref in grads.items():
-        if "_1/" in k or k.startswith("DecoderPrep"):
+        if ("_1/" in k or k.startswith("DecoderPrep")) and "KeyProjection/bias" not in k:      # (key bias: mathematically zero)
             assert nerr(g[k], ref, 1e-6 * max(float(np.abs(v).max()) for v in grads.values())) < 5e-4, k
