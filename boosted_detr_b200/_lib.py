@@ -33,6 +33,14 @@ FfnScratch = _ptr_struct("FfnScratch", ["d_z", "d_h"])
 HeadParams = _ptr_struct("HeadParams", ["w1", "b1", "bn_gamma", "bn_beta", "bn_moving_mean", "bn_moving_var", "w2", "b2"])
 HeadSaved = _ptr_struct("HeadSaved", ["h", "hn", "bn_mean", "bn_rstd", "bn_acc", "act"])
 HeadScratch = _ptr_struct("HeadScratch", ["d_logits", "d_hn", "d_h"])
+HeadsSaved = _ptr_struct("HeadsSaved", ["h", "bn_mean", "bn_rstd", "w2f", "b2f", "bn_part", "act0", "act1", "act2"])
+HeadsScratch = _ptr_struct("HeadsScratch", ["d_logits", "hTd", "colsum_d", "bn_s", "d_h"])
+PTR3 = c_void_p * 3
+INT3 = c_int * 3
+
+
+class PosFold(Structure):
+    _fields_ = [("pos", c_void_p), ("tab_q", c_void_p), ("tab_k", c_void_p), ("resid_pos", c_int), ("pos_tc", c_void_p)]
 
 P = c_void_p
 I = c_int
@@ -79,6 +87,21 @@ PROTOTYPES = {
     "bdetr_head_bwd": (c_int, [I, I, I, I, I, I, F, P, POINTER(HeadParams), F, POINTER(HeadSaved), P, P, I,
                                POINTER(HeadParams), POINTER(HeadScratch), P]),
     "bdetr_gemm": (c_int, [I, I, I, P, I, P, I, P, I, I, P, P]),
+    "bdetr_pos_projection": (c_int, [I, I, P, I, POINTER(PTR3), POINTER(PTR3), POINTER(PTR3), P]),
+    "bdetr_attention_fused_fwd": (c_int, [I, I, I, I, I, P, P, POINTER(PosFold), POINTER(AttnParams), F, c_uint32, P, F, I, P,
+                                          POINTER(AttnSaved), P]),
+    "bdetr_attention_fused_bwd": (c_int, [I, I, I, I, I, P, P, POINTER(PosFold), POINTER(AttnParams), F, c_uint32, P,
+                                          POINTER(AttnSaved), P, P, P, I, P, POINTER(AttnParams), POINTER(AttnScratch), P, P, P]),
+    "bdetr_ffn_fused_fwd": (c_int, [I, I, P, POINTER(FfnParams), F, c_uint32, P, F, I, P, POINTER(FfnSaved), P]),
+    "bdetr_ffn_fused_bwd": (c_int, [I, I, P, POINTER(FfnParams), F, c_uint32, P, POINTER(FfnSaved), P, P, I,
+                                    POINTER(FfnParams), POINTER(FfnScratch), P]),
+    "bdetr_decoder_self_fwd": (c_int, [I, I, I, I, P, P, POINTER(AttnParams), F, c_uint32, P, F, I, P, POINTER(AttnSaved), P, P]),
+    "bdetr_decoder_self_bwd": (c_int, [I, I, I, I, P, P, POINTER(AttnParams), F, c_uint32, P, POINTER(AttnSaved), P, P,
+                                       POINTER(AttnParams), POINTER(AttnScratch), P, P, P]),
+    "bdetr_heads_fwd": (c_int, [I, I, I, I, I, P, POINTER(HeadParams), POINTER(INT3), F, F, F, POINTER(PTR3), POINTER(PTR3),
+                                POINTER(HeadsSaved), P]),
+    "bdetr_heads_bwd": (c_int, [I, I, I, I, I, P, POINTER(HeadParams), POINTER(INT3), F, POINTER(HeadsSaved), POINTER(PTR3), P, I,
+                                POINTER(PTR3), POINTER(HeadsScratch), P]),
 }
 
 _lib = None

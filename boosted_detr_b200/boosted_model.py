@@ -13,6 +13,7 @@ train_step / test_step (which, as in the reference :269-270, also trains), per-b
 """
 from __future__ import annotations
 
+import os
 import re
 
 import numpy as np
@@ -22,8 +23,10 @@ from . import _lib
 from .device import empty, f32, i32, ptr, require_cuda, stream_ptr, zeros
 from .layers import Layer, dropout_key, dropout_site_key
 from .losses_and_metrics import MatchingLoss, PreparedTargets, raise_for_status
-from .prediction_heads import BoxPredictionHead, MultiClassPredictionHead, SingleClassPredictionHead
-from .transformers import (DecoderBlock, DecoderBlock_NoSelfAttention, DecoderPrep, ImageEncoderAttention, accumulate)
+from .prediction_heads import (BoxPredictionHead, MultiClassPredictionHead, SingleClassPredictionHead, heads_backward_fused,
+                               heads_forward_fused)
+from .transformers import (DecoderBlock, DecoderBlock_NoSelfAttention, DecoderPrep, ImageEncoderAttention, accumulate,
+                           batch_sum_into, fused_path, make_fold, pos_projection)
 
 # dropout site ids, one per Keras Dropout instance: block i -> 8*i + k
 SITE_ENC_ATTN, SITE_ENC_FFN, SITE_DEC_SELF, SITE_DEC_CROSS, SITE_DEC_FFN = 0, 1, 2, 3, 4
@@ -133,7 +136,7 @@ class BoostedDETR:
             flat_w[o0:o0 + cnt].copy_(o._weights[k].reshape(-1))
             o._weights[k] = flat_w[o0:o0 + cnt].view(shp)
             o._grads[k] = flat_g[o0:o0 + cnt].view(shp)
-            if k.endswith("/kernel"):
+            if k.endswith("/kernel") or k in ("positional_encoding", "init_decoder_features"):
                 o._shadow[k] = flat_tc[o0:o0 + cnt].view(shp)     # tf32-rounded copy read by the tcgen05 GEMMs
         self._flat = (flat_w, flat_g)
         self._flat_tc = flat_tc
@@ -279,6 +282,202 @@ class BoostedDETR:
         ev.record(stream if stream is not None else torch.cuda.current_stream())
         tr.append((label, ev))
 
+    # -- fused tensor-core path -------------------------------------------------------------------
+    def _use_fused(self, feats):
+        """Tensor-core mode, model width 256, every layer already built (the very first call builds the layers lazily
+        in the reference's execution order, which fixes the seeded initial weights -- it runs the layer-level path) and
+        enough rows per GEMM for one 128-row tile."""
+        if self._flat is None or not fused_path(self.encoder_dim) or self.decoder_dim != 256:
+            return False
+        B, R, Cc, _ = feats.shape
+        return B * R * Cc >= 128 and B * self.num_object_preds >= 128 and os.environ.get("BDETR_FUSED", "1") == "1"
+
+    def _forward_fused(self, feats, y_true, training):
+        """Same hot loop as `forward` on the fused entry points (include/bdetr.h "Fused tensor-core path"):
+            aux2   positional tables pos W + b of every block (batch-invariant) and the decoder self-attention of blocks
+                   >= 1 hoisted out of the batch -- both depend on the weights only and run ahead of everything
+            main   encoder i: grouped q/k/v projection -> attention -> out-proj+LN -> DenseRelu -> DenseLinear+LN
+            dec    decoder i (q projection beside the grouped k/v projection -> attention -> out-proj+LN -> FFN),
+                   the three heads in one call, then the matching of block i on its own stream"""
+        N = self.num_decoder_blocks
+        use_dropout = training and self.dropout_seed is not None
+        if use_dropout and not torch.cuda.is_current_stream_capturing():
+            self.push_dropout_seed()
+        seed_dev = self._seed_dev if use_dropout else None
+        rate = 0.1 if use_dropout else 0.0
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if training else None
+        aux = self._aux_streams()
+        dec_s, pre_s = aux[3], aux[2]
+        self.refresh_shadow()
+        x = torch.empty_like(feats)                        # the block input feeds tcgen05 GEMMs: round it too
+        _lib.call("bdetr_round_tf32", feats.numel(), ptr(feats), ptr(x), stream_ptr())
+        B, R, Cc, D = feats.shape
+        L, Q = R * Cc, self.num_object_preds
+        prepared, loss_streams = None, None
+        if training:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                prepared = PreparedTargets(y_true)
+            loss_streams = self._loss_streams(N)
+            for ls in loss_streams:
+                ls.wait_stream(side)
+        # ---- weight-only work, ahead of the image-dependent chains ------------------------------------------------
+        q0 = self.DecoderPrep._weights["init_decoder_features"]
+        q0_tc = self.DecoderPrep._shadow.get("init_decoder_features", q0)
+        pre_s.wait_stream(main)
+        tabs, pre_self, pre_ev = [], [], []
+        with torch.cuda.stream(pre_s):
+            dec0 = self.DecoderPrep.tile_queries(B)         # block 0's decoder input: the tiled queries (:445-447)
+            for i in range(N):
+                enc, dec_l = self.EncoderTransformerBlocks[i], self.DecoderBlocks[i]
+                for nm in ("SelfAttentionBlock", "JointAttentionBlock", "FeedForwardBlock"):
+                    if hasattr(dec_l, nm):
+                        getattr(dec_l, nm).rate = rate
+                blk = enc.EncoderBlocks[0]
+                blk.SelfAttentionBlock.rate = blk.FeedForwardBlock.rate = rate
+                tabs.append(pos_projection(enc.pos_tc(), [(blk.SelfAttentionBlock.AttentionLayer, "QueryProjection"),
+                                                          (blk.SelfAttentionBlock.AttentionLayer, "KeyProjection"),
+                                                          (dec_l.JointAttentionBlock.AttentionLayer, "KeyProjection")]))
+                keys = self._keys(i) if use_dropout else None
+                if i >= 1:
+                    pre_self.append(dec_l.SelfAttentionBlock.forward_hoisted(q0, q0_tc, B, training, keys["dec"][0] if keys else 0, seed_dev))
+                else:
+                    pre_self.append(None)
+                ev = torch.cuda.Event()
+                ev.record(pre_s)
+                pre_ev.append(ev)
+        cums = None
+        blocks, loss_ctxs = [], []
+        for i in range(N):
+            keys = self._keys(i) if use_dropout else None
+            enc, dec_l = self.EncoderTransformerBlocks[i], self.DecoderBlocks[i]
+            dkeys = keys["dec"] if keys else (0, 0, 0)
+            main.wait_event(pre_ev[i])
+            (x, pos), c_enc = enc.forward([x], training, keys["enc"] if keys else None, seed_dev, tabs=tabs[i][:2])
+            self._mark(f"fwd enc{i} done (main)")
+            dec_s.wait_stream(main)
+            with torch.cuda.stream(dec_s):
+                fold = make_fold(pos=pos.view(L, D), tab_k=tabs[i][2], pos_tc=enc.pos_tc())
+                dec_in = dec0 if i == 0 else pre_self[i][0]
+                dec, c_dec = dec_l.forward_fused(x.view(B, L, D), fold, dec_in, training, dkeys, seed_dev)
+                self._mark(f"fwd dec{i} done (dec)")
+                mult = 2.0 if i == 0 else 1.0                 # block 0 is counted twice (reference :222-229)
+                heads = (self.CategoryBlocks[i], self.AttributeBlocks[i], self.BoxBlocks[i])
+                cums, c_heads = heads_forward_fused(heads, dec, training, cums, mult)
+                self._mark(f"fwd heads{i} done (dec)")
+                blocks.append({"enc": c_enc, "dec": c_dec, "self": None if i == 0 else pre_self[i][1], "heads": c_heads, "dec0": dec0})
+                if training:
+                    ls = loss_streams[i]
+                    ls.wait_stream(dec_s)
+                    with torch.cuda.stream(ls):
+                        loss_ctxs.append(self.loss_fn.forward(y_true, cums, prepared))
+                        self._mark(f"fwd loss{i} done (side)")
+        main.wait_stream(dec_s)
+        main.wait_stream(pre_s)
+        if training:
+            main.wait_stream(side)
+            for ls in loss_streams:
+                main.wait_stream(ls)
+        self._mark("fwd joined (main)")
+        return cums, {"blocks": blocks, "loss": loss_ctxs, "y_true": y_true, "fused": True}
+
+    def _trainable_flags(self):
+        N = self.num_decoder_blocks
+        enc = [self.EncoderTransformerBlocks[i].trainable for i in range(N)]
+        dec = [self.DecoderBlocks[i].trainable for i in range(N)]
+        heads = [any(h[i].trainable for h in (self.CategoryBlocks, self.AttributeBlocks, self.BoxBlocks)) for i in range(N)]
+        return enc, dec, heads, self.DecoderPrep.trainable
+
+    def _backward_fused(self, ctx, gscale=1.0):
+        """Backward of `_forward_fused`.  Work nothing trainable depends on is skipped (the reference's boosted
+        training regime freezes whole blocks, Boosted_DETR_COCO.ipynb cell 30): no parameter gradients for frozen
+        layers, no data gradients into blocks below the first trainable one."""
+        N = self.num_decoder_blocks
+        first = ctx["loss"][0]
+        B, T, Q, C, A = first["dims"]
+        enc_tr, dec_tr, heads_tr, prep_tr = self._trainable_flags()
+        # does anything trainable sit at or below encoder i (on the chain x_0 -> enc_0 -> enc_1 -> ...)?
+        below = [any(enc_tr[:i + 1]) for i in range(N)]
+        r_cat, r_attr, r_box = zeros(B, Q, C), zeros(B, Q, A), zeros(B, Q, 4)
+        main = torch.cuda.current_stream()
+        aux = self._aux_streams()
+        dec_s, pre_s = aux[3], aux[2]
+        keep = [r_cat, r_attr, r_box]
+        dec_s.wait_stream(main)
+        pre_s.wait_stream(main)
+        g_q0 = self.DecoderPrep._grads["init_decoder_features"]
+        d_encs, evs, self_evs = [None] * N, [None] * N, [None] * N
+
+        def decoder_side(i):
+            blk = ctx["blocks"][i]
+            dec_l = self.DecoderBlocks[i]
+            enc = self.EncoderTransformerBlocks[i]
+            with torch.cuda.stream(dec_s):
+                self.loss_fn.backward(ctx["loss"][i], r_cat, r_attr, r_box, gscale)
+                self._mark(f"bwd loss{i} done (dec)")
+                self_tr = i >= 1 and dec_l.SelfAttentionBlock.trainable
+                need_d_dec = prep_tr or self_tr
+                need_d_enc = below[i]
+                need_dec = dec_tr[i] or need_d_dec or need_d_enc
+                d_dec = None
+                if heads_tr[i] or need_dec:
+                    heads = (self.CategoryBlocks[i], self.AttributeBlocks[i], self.BoxBlocks[i])
+                    d_dec = heads_backward_fused(heads, blk["heads"], [r_cat, r_attr, r_box], need_dx=need_dec)
+                self._mark(f"bwd heads{i} done (dec)")
+                d_dec_in = d_enc = None
+                if need_dec:
+                    L, D = blk["dec"]["joint"]["dims"][2], blk["dec"]["joint"]["dims"][3]
+                    g_pos = enc._grads["positional_encoding"].view(L, D)
+                    d_dec_in, d_enc = dec_l.backward_fused(blk["dec"], d_dec, d_pos=g_pos if enc.trainable else None,
+                                                           need_d_dec=need_d_dec, need_d_enc=need_d_enc)
+                if d_dec_in is not None:
+                    pre_s.wait_stream(dec_s)
+                    with torch.cuda.stream(pre_s):                       # query-parameter side: queries only
+                        if i == 0:
+                            if prep_tr:
+                                batch_sum_into(d_dec_in, g_q0)
+                        else:
+                            dec_l.SelfAttentionBlock.backward_hoisted(blk["self"], d_dec_in, g_q0 if prep_tr else None)
+                sev = torch.cuda.Event()
+                sev.record(pre_s)
+                self_evs[i] = sev
+                ev = torch.cuda.Event()
+                ev.record(dec_s)
+                evs[i] = ev
+                d_encs[i] = d_enc
+                self._mark(f"bwd dec{i} done (dec)")
+                keep.extend([d_dec, d_dec_in, d_enc])
+
+        decoder_side(N - 1)
+        for i in reversed(range(N)):
+            if i > 0:
+                decoder_side(i - 1)          # enqueued before encoder i: encoder i accumulates its input gradient into d_enc[i-1]
+            main.wait_event(evs[i])
+            self._mark(f"bwd enc{i} may start (main)")
+            enc = self.EncoderTransformerBlocks[i]
+            d_out = d_encs[i]                # gradient of encoder i's output: decoder i's k/v paths (+ encoder i+1, accumulated)
+            if d_out is not None and (enc.trainable or (i > 0 and below[i - 1])):
+                Bf, L, D = d_out.shape
+                R, Cc = self.feature_shape
+                need_dx = i > 0 and below[i - 1]
+                tgt = d_encs[i - 1] if need_dx else None
+                if need_dx:
+                    main.wait_event(evs[i - 1])                       # d_enc[i-1] must exist before it is accumulated into
+                enc.backward(ctx["blocks"][i]["enc"], d_out.view(Bf, R, Cc, D), d_x=None if tgt is None else tgt.view(Bf, R, Cc, D),
+                             acc=tgt is not None, need_dx=need_dx)
+            self._mark(f"bwd enc{i} done (main)")
+            if self.grad_bucket_hook is not None and self._flat is not None:
+                _, lo, hi = self._buckets[N - 1 - i]
+                hook_evs = [self_evs[i]]
+                if i == 0:
+                    hook_evs = [e for e in self_evs if e is not None]
+                self.grad_bucket_hook(i, lo, hi, hook_evs)
+        main.wait_stream(dec_s)
+        main.wait_stream(pre_s)
+        self._mark("bwd joined (main)")
+        return None
+
     # -- forward -------------------------------------------------------------------------------
     def forward(self, feats, y_true, training):
         """The hot loop (reference :199-246).  Returns (y_pred, ctx).
@@ -293,6 +492,8 @@ class BoostedDETR:
             aux2     decoder self-attention of block i >= 1 (queries only: no dependency on the image at all)
             side     cost matrix -> per-image assignment -> matched loss of block i (forked from dec)
         and everything is joined into main before returning."""
+        if self._use_fused(feats):
+            return self._forward_fused(feats, y_true, training)
         N = self.num_decoder_blocks
         use_dropout = training and self.dropout_seed is not None
         if use_dropout and not torch.cuda.is_current_stream_capturing():
@@ -387,6 +588,8 @@ class BoostedDETR:
         running prediction gradient, not on the encoder backward, so that chain runs ahead on the `dec` stream
         (heads on aux0/1, decoder self-attention backward on aux2) and hands (d_enc_value, d_enc_key) of block i
         to the encoder chain on the main stream through an event."""
+        if ctx.get("fused"):
+            return self._backward_fused(ctx, gscale)
         N = self.num_decoder_blocks
         first = ctx["loss"][0]
         B, T, Q, C, A = first["dims"]

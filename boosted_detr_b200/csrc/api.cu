@@ -20,7 +20,10 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
-int current_mode() { return g_mode.load(std::memory_order_relaxed); }
+static thread_local int t_mode_override = -1;
+int current_mode() { return t_mode_override >= 0 ? t_mode_override : g_mode.load(std::memory_order_relaxed); }
+ModeScope::ModeScope(int mode) : saved(t_mode_override) { t_mode_override = mode; }
+ModeScope::~ModeScope() { t_mode_override = saved; }
 
 // ---- auxiliary stream pool (per device) ---------------------------------------------------------------------
 static std::atomic<int> g_conc{1};

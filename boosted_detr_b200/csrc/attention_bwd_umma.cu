@@ -355,7 +355,7 @@ bool attention_bwd_umma_eligible(int B, int H, int Lq, int Lk, int d, const floa
                                  const float *d_o)
 {
     auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    return d == FB_HD && al(qp) && al(kp) && al(vp) && al(d_o) && (long long)B * Lq >= FB_ROWS && (long long)B * Lk >= FB_ROWS;
+    return d == FB_HD && al(qp) && al(kp) && al(vp) && al(d_o) && B >= 1 && Lq >= 1 && Lk >= 1;
 }
 
 int launch_attention_bwd_umma(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,

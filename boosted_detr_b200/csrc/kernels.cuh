@@ -5,6 +5,12 @@
 namespace bdetr {
 
 int current_mode();
+// Entry points that ARE one compute mode (the fused tensor-core path) pin it for the calling thread while they run.
+struct ModeScope {
+    explicit ModeScope(int mode);
+    ~ModeScope();
+    int saved;
+};
 
 // Fork / join of independent kernel chains onto library-owned auxiliary streams.  The kernels of this workload
 // are short and at most ~100 CTAs wide, so independent ones (wgrad next to dgrad, the q/k/v projections) are
@@ -33,6 +39,23 @@ bool umma_gemm_eligible(int M, int N, int K, const float *A, int lda, bool TA, c
 int launch_gemm_umma(int M, int N, int K, const float *A, int lda, bool TA, const float *B, int ldb, bool TB,
                      const float *bias, int act, const float *relu_mask, int beta, int round_out, float *C, int ldc,
                      cudaStream_t s);
+
+// Up to three tcgen05 GEMMs of identical shape [M,N,K] in one launch (gemm_umma.cu).
+//   sum_groups = false: independent outputs C[g] = op(A[share_a ? 0 : g]) op(B[g]) (+ bias[g]) (+ rowtab[g]) ...
+//   sum_groups = true : ONE output C[0] = sum_g op(A[g]) op(B[g])  (the k loop runs over all groups)
+// rowtab[g]: out[r,n] += rowtab[g][(r % rowtab_period) * rowtab_ld + n]; colsum[g][n] += column sums of the stored output.
+struct GroupedGemm {
+    int M = 0, N = 0, K = 0, groups = 1;
+    bool TA = false, TB = false, share_a = false, sum_groups = false;
+    const float *A[3] = {nullptr, nullptr, nullptr}; int lda = 0;
+    const float *B[3] = {nullptr, nullptr, nullptr}; int ldb = 0;
+    float *C[3] = {nullptr, nullptr, nullptr}; int ldc = 0;
+    const float *bias[3] = {nullptr, nullptr, nullptr};
+    const float *rowtab[3] = {nullptr, nullptr, nullptr}; int rowtab_period = 0, rowtab_ld = 0;
+    float *colsum[3] = {nullptr, nullptr, nullptr};
+    int act = 0; const float *relu_mask = nullptr; int beta = 0; int round_out = 0;
+};
+int launch_gemm_umma_grouped(const GroupedGemm &g, cudaStream_t s);
 
 // dst[n] += sum_m src[m, n]
 int launch_colsum_acc(int M, int N, const float *src, float *dst, cudaStream_t s);
@@ -68,6 +91,21 @@ int launch_res_ln_fwd(int M, int D, const float *resid, float *z, const float *g
 int launch_res_ln_bwd(int M, int D, const float *d_out, const float *z, const float *mean, const float *rstd,
                       const float *gamma, float rate, uint32_t key, const uint32_t *seed_dev, float *d_resid, int acc_resid,
                       float *d_a, float *g_gamma, float *g_beta, float *g_bias, int round_out, cudaStream_t s);
+
+int launch_res_ln_bcast_fwd(int M, int P, int D, const float *resid, const float *a, float *z, const float *gamma, const float *beta,
+                            float eps, float rate, uint32_t key, const uint32_t *seed_dev, float *out, float *mean, float *rstd,
+                            int round_out, cudaStream_t s);
+struct BatchReduce {
+    int n = 0, B = 0, D = 0;
+    const float *src[4] = {nullptr, nullptr, nullptr, nullptr}; int rows[4] = {0, 0, 0, 0};
+    float *sum[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *colsum[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+int launch_batch_reduce(const BatchReduce &a, cudaStream_t s);
+// Dense + bias + Dropout + residual (+ pos rows) + LayerNorm in one tcgen05 kernel (gemm_ln.cu); z may be NULL (not saved)
+int launch_gemm_ln(int M, int K, const float *A, const float *W, const float *bias, const float *resid, const float *pos,
+                   int pos_period, const float *gamma, const float *beta, float eps, float rate, uint32_t key,
+                   const uint32_t *seed_dev, float *z, float *out, float *mean, float *rstd, int round_out, cudaStream_t s);
 
 int launch_add_rows_fwd(int B, int L, int D, const float *x, const float *pos, float *out, int round_out, cudaStream_t s);
 int launch_batch_sum_acc(int B, int L, int D, const float *src, float *dst, cudaStream_t s);

