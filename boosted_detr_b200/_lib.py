@@ -55,6 +55,8 @@ PROTOTYPES = {
     "bdetr_set_pdl": (c_int, [I]),
     "bdetr_set_concurrency": (c_int, [I]),
     "bdetr_get_concurrency": (c_int, []),
+    "bdetr_set_deferred_join": (c_int, [I]),
+    "bdetr_join": (c_int, [P]),
     "bdetr_get_pdl": (c_int, []),
     "bdetr_launch_count": (c_longlong, []),
     "bdetr_reset_launch_count": (None, []),
@@ -79,6 +81,7 @@ PROTOTYPES = {
     "bdetr_add_positional_bwd": (c_int, [I, I, I, P, P, P]),
     "bdetr_tile_queries_fwd": (c_int, [I, I, I, P, P, P]),
     "bdetr_accumulate": (c_int, [c_size_t, P, P, P]),
+    "bdetr_suffix_sum": (c_int, [I, c_size_t, P, P]),
     "bdetr_sgd_step": (c_int, [I, P, P, P, P, P, F, P, F, I, F, P]),
     "bdetr_round_tf32": (c_int, [c_size_t, P, P, P]),
     "bdetr_debug_set_timeline": (c_int, [P]),

@@ -264,6 +264,33 @@ class BoostedDETR:
         self._loss_s = cur
         return cur[:n]
 
+    def _block_streams(self, n, backward=False):
+        """One side stream per boosted block (decoder / heads / matching of block i; their backward).  Backward: the
+        chains are needed by the sequential encoder chain in the order N-1, N-2, ... -- their stream priorities follow
+        that order (pending CTAs of a higher-priority kernel are placed first when SM slots free up)."""
+        if not _lib.load().bdetr_get_concurrency():
+            return [torch.cuda.current_stream()] * n
+        key = "_blk_bw" if backward else "_blk_s"
+        cur = getattr(self, key, [])
+        use_prio = os.environ.get("BDETR_STREAM_PRIORITY", "0") == "1"
+        while len(cur) < n:
+            prio = 0
+            if backward and use_prio:
+                rank = n - 1 - len(cur)                       # 0 = needed first (block N-1)
+                prio = min(-1, -4 + rank)                     # -4, -3, -2, -1, -1, ...
+            cur.append(torch.cuda.Stream(priority=prio))
+        setattr(self, key, cur)
+        return cur[:n]
+
+    def _critical_stream(self):
+        """The sequential encoder chain runs on a highest-priority stream: it is the step's critical path, and its
+        ~100-CTA kernels otherwise queue for SM slots behind the decoder / heads / matcher kernels of other blocks."""
+        if not _lib.load().bdetr_get_concurrency() or os.environ.get("BDETR_STREAM_PRIORITY", "0") != "1":
+            return None
+        if getattr(self, "_crit", None) is None:
+            self._crit = torch.cuda.Stream(priority=-5)
+        return self._crit
+
     def _aux_streams(self):
         """Four extra streams: two for the attribute / box heads (the three heads of a block are independent
         chains of short kernels), one for the batch-invariant decoder self-attention, one for the decoder chain."""
@@ -305,6 +332,18 @@ class BoostedDETR:
             self.push_dropout_seed()
         seed_dev = self._seed_dev if use_dropout else None
         rate = 0.1 if use_dropout else 0.0
+        caller = torch.cuda.current_stream()
+        crit = self._critical_stream()
+        if crit is not None:
+            crit.wait_stream(caller)
+            with torch.cuda.stream(crit):
+                out = self._forward_fused_on(feats, y_true, training, use_dropout, seed_dev, rate)
+            caller.wait_stream(crit)
+            return out
+        return self._forward_fused_on(feats, y_true, training, use_dropout, seed_dev, rate)
+
+    def _forward_fused_on(self, feats, y_true, training, use_dropout, seed_dev, rate):
+        N = self.num_decoder_blocks
         main = torch.cuda.current_stream()
         side = self._side_stream() if training else None
         aux = self._aux_streams()
@@ -319,9 +358,8 @@ class BoostedDETR:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 prepared = PreparedTargets(y_true)
-            loss_streams = self._loss_streams(N)
-            for ls in loss_streams:
-                ls.wait_stream(side)
+            for bs in self._block_streams(N):
+                bs.wait_stream(side)
         # ---- weight-only work, ahead of the image-dependent chains ------------------------------------------------
         q0 = self.DecoderPrep._weights["init_decoder_features"]
         q0_tc = self.DecoderPrep._shadow.get("init_decoder_features", q0)
@@ -349,6 +387,10 @@ class BoostedDETR:
                 pre_ev.append(ev)
         cums = None
         blocks, loss_ctxs = [], []
+        # decoder i / heads i / matching i hang off encoder i's output only (plus the running prediction of block i-1):
+        # every block gets its own side stream, so decoder i overlaps heads i-1 and the matchings
+        bstreams = self._block_streams(N)
+        heads_ev = None
         for i in range(N):
             keys = self._keys(i) if use_dropout else None
             enc, dec_l = self.EncoderTransformerBlocks[i], self.DecoderBlocks[i]
@@ -356,29 +398,30 @@ class BoostedDETR:
             main.wait_event(pre_ev[i])
             (x, pos), c_enc = enc.forward([x], training, keys["enc"] if keys else None, seed_dev, tabs=tabs[i][:2])
             self._mark(f"fwd enc{i} done (main)")
-            dec_s.wait_stream(main)
-            with torch.cuda.stream(dec_s):
+            bs = bstreams[i]
+            bs.wait_stream(main)
+            with torch.cuda.stream(bs):
                 fold = make_fold(pos=pos.view(L, D), tab_k=tabs[i][2], pos_tc=enc.pos_tc())
                 dec_in = dec0 if i == 0 else pre_self[i][0]
                 dec, c_dec = dec_l.forward_fused(x.view(B, L, D), fold, dec_in, training, dkeys, seed_dev)
                 self._mark(f"fwd dec{i} done (dec)")
                 mult = 2.0 if i == 0 else 1.0                 # block 0 is counted twice (reference :222-229)
                 heads = (self.CategoryBlocks[i], self.AttributeBlocks[i], self.BoxBlocks[i])
+                if heads_ev is not None:
+                    bs.wait_event(heads_ev)                   # the running prediction of block i-1
                 cums, c_heads = heads_forward_fused(heads, dec, training, cums, mult)
+                heads_ev = torch.cuda.Event()
+                heads_ev.record(bs)
                 self._mark(f"fwd heads{i} done (dec)")
                 blocks.append({"enc": c_enc, "dec": c_dec, "self": None if i == 0 else pre_self[i][1], "heads": c_heads, "dec0": dec0})
                 if training:
-                    ls = loss_streams[i]
-                    ls.wait_stream(dec_s)
-                    with torch.cuda.stream(ls):
-                        loss_ctxs.append(self.loss_fn.forward(y_true, cums, prepared))
-                        self._mark(f"fwd loss{i} done (side)")
-        main.wait_stream(dec_s)
+                    loss_ctxs.append(self.loss_fn.forward(y_true, cums, prepared))
+                    self._mark(f"fwd loss{i} done (side)")
+        for bs in bstreams:
+            main.wait_stream(bs)
         main.wait_stream(pre_s)
         if training:
             main.wait_stream(side)
-            for ls in loss_streams:
-                main.wait_stream(ls)
         self._mark("fwd joined (main)")
         return cums, {"blocks": blocks, "loss": loss_ctxs, "y_true": y_true, "fused": True}
 
@@ -390,32 +433,70 @@ class BoostedDETR:
         return enc, dec, heads, self.DecoderPrep.trainable
 
     def _backward_fused(self, ctx, gscale=1.0):
+        caller = torch.cuda.current_stream()
+        crit = self._critical_stream()
+        if crit is not None:
+            crit.wait_stream(caller)
+            with torch.cuda.stream(crit):
+                self._backward_fused_on(ctx, gscale)
+            caller.wait_stream(crit)
+            return None
+        return self._backward_fused_on(ctx, gscale)
+
+    def _backward_fused_on(self, ctx, gscale=1.0):
         """Backward of `_forward_fused`.  Work nothing trainable depends on is skipped (the reference's boosted
         training regime freezes whole blocks, Boosted_DETR_COCO.ipynb cell 30): no parameter gradients for frozen
         layers, no data gradients into blocks below the first trainable one."""
+        lib = _lib.load()
+        # parameter-gradient side chains are joined once per block (bdetr_join below), not inside every layer call
+        lib.bdetr_set_deferred_join(1 if os.environ.get("BDETR_DEFER_JOIN", "1") == "1" else 0)
+        try:
+            return self._backward_fused_body(ctx, gscale)
+        finally:
+            lib.bdetr_set_deferred_join(0)
+
+    def _backward_fused_body(self, ctx, gscale):
         N = self.num_decoder_blocks
         first = ctx["loss"][0]
         B, T, Q, C, A = first["dims"]
         enc_tr, dec_tr, heads_tr, prep_tr = self._trainable_flags()
         # does anything trainable sit at or below encoder i (on the chain x_0 -> enc_0 -> enc_1 -> ...)?
         below = [any(enc_tr[:i + 1]) for i in range(N)]
-        r_cat, r_attr, r_box = zeros(B, Q, C), zeros(B, Q, A), zeros(B, Q, 4)
+        # Gradient of the running prediction of block i = sum of the loss gradients of blocks i .. N-1 (every later block's
+        # prediction contains it).  The N loss backward kernels only need forward quantities, so they all run at once,
+        # each into its own slice of one zeroed buffer, and one suffix-sum kernel turns the slices into the running
+        # gradients; after that the heads / decoder backward of ALL blocks are independent chains (one stream each) --
+        # only the encoder chain on the main stream is sequential.
+        nC, nA, nB = B * Q * C, B * Q * A, B * Q * 4
+        per = nC + nA + nB
+        RG = zeros(N, per)
+        r_of = lambda i: (RG[i, :nC].view(B, Q, C), RG[i, nC:nC + nA].view(B, Q, A), RG[i, nC + nA:].view(B, Q, 4))
         main = torch.cuda.current_stream()
         aux = self._aux_streams()
-        dec_s, pre_s = aux[3], aux[2]
-        keep = [r_cat, r_attr, r_box]
-        dec_s.wait_stream(main)
+        pre_s = aux[2]
+        bstreams = self._block_streams(N, backward=True)
+        keep = [RG]
         pre_s.wait_stream(main)
+        for i in range(N):
+            bstreams[i].wait_stream(main)
+            with torch.cuda.stream(bstreams[i]):
+                self.loss_fn.backward(ctx["loss"][i], *r_of(i), gscale)
+        for i in range(1, N):
+            bstreams[0].wait_stream(bstreams[i])
+        with torch.cuda.stream(bstreams[0]):
+            _lib.call("bdetr_suffix_sum", N, per, ptr(RG), stream_ptr())
+            self._mark("bwd loss gradients done (dec)")
+        for i in range(1, N):
+            bstreams[i].wait_stream(bstreams[0])
         g_q0 = self.DecoderPrep._grads["init_decoder_features"]
-        d_encs, evs, self_evs = [None] * N, [None] * N, [None] * N
+        d_encs, evs, self_evs, grad_evs = [None] * N, [None] * N, [None] * N, [None] * N
 
         def decoder_side(i):
             blk = ctx["blocks"][i]
             dec_l = self.DecoderBlocks[i]
             enc = self.EncoderTransformerBlocks[i]
+            dec_s = bstreams[i]
             with torch.cuda.stream(dec_s):
-                self.loss_fn.backward(ctx["loss"][i], r_cat, r_attr, r_box, gscale)
-                self._mark(f"bwd loss{i} done (dec)")
                 self_tr = i >= 1 and dec_l.SelfAttentionBlock.trainable
                 need_d_dec = prep_tr or self_tr
                 need_d_enc = below[i]
@@ -423,7 +504,7 @@ class BoostedDETR:
                 d_dec = None
                 if heads_tr[i] or need_dec:
                     heads = (self.CategoryBlocks[i], self.AttributeBlocks[i], self.BoxBlocks[i])
-                    d_dec = heads_backward_fused(heads, blk["heads"], [r_cat, r_attr, r_box], need_dx=need_dec)
+                    d_dec = heads_backward_fused(heads, blk["heads"], list(r_of(i)), need_dx=need_dec)
                 self._mark(f"bwd heads{i} done (dec)")
                 d_dec_in = d_enc = None
                 if need_dec:
@@ -431,6 +512,9 @@ class BoostedDETR:
                     g_pos = enc._grads["positional_encoding"].view(L, D)
                     d_dec_in, d_enc = dec_l.backward_fused(blk["dec"], d_dec, d_pos=g_pos if enc.trainable else None,
                                                            need_d_dec=need_d_dec, need_d_enc=need_d_enc)
+                ev = torch.cuda.Event()
+                ev.record(dec_s)                                          # data gradients of block i's decoder side are final
+                evs[i] = ev
                 if d_dec_in is not None:
                     pre_s.wait_stream(dec_s)
                     with torch.cuda.stream(pre_s):                       # query-parameter side: queries only
@@ -439,12 +523,15 @@ class BoostedDETR:
                                 batch_sum_into(d_dec_in, g_q0)
                         else:
                             dec_l.SelfAttentionBlock.backward_hoisted(blk["self"], d_dec_in, g_q0 if prep_tr else None)
-                sev = torch.cuda.Event()
-                sev.record(pre_s)
+                            _lib.call("bdetr_join", stream_ptr())
+                with torch.cuda.stream(pre_s):
+                    sev = torch.cuda.Event()
+                    sev.record(pre_s)
                 self_evs[i] = sev
-                ev = torch.cuda.Event()
-                ev.record(dec_s)
-                evs[i] = ev
+                _lib.call("bdetr_join", stream_ptr())                    # parameter gradients of decoder i / heads i
+                gev = torch.cuda.Event()
+                gev.record(dec_s)
+                grad_evs[i] = gev
                 d_encs[i] = d_enc
                 self._mark(f"bwd dec{i} done (dec)")
                 keep.extend([d_dec, d_dec_in, d_enc])
@@ -468,12 +555,15 @@ class BoostedDETR:
                              acc=tgt is not None, need_dx=need_dx)
             self._mark(f"bwd enc{i} done (main)")
             if self.grad_bucket_hook is not None and self._flat is not None:
+                _lib.call("bdetr_join", stream_ptr())                    # encoder i's parameter gradients
                 _, lo, hi = self._buckets[N - 1 - i]
-                hook_evs = [self_evs[i]]
+                hook_evs = [self_evs[i], grad_evs[i]]
                 if i == 0:
-                    hook_evs = [e for e in self_evs if e is not None]
+                    hook_evs = [e for e in self_evs if e is not None] + [grad_evs[0]]
                 self.grad_bucket_hook(i, lo, hi, hook_evs)
-        main.wait_stream(dec_s)
+        _lib.call("bdetr_join", stream_ptr())
+        for bs in bstreams:
+            main.wait_stream(bs)
         main.wait_stream(pre_s)
         self._mark("bwd joined (main)")
         return None

@@ -28,8 +28,10 @@ ModeScope::~ModeScope() { t_mode_override = saved; }
 // ---- auxiliary stream pool (per device) ---------------------------------------------------------------------
 static std::atomic<int> g_conc{1};
 bool concurrency_enabled() { return g_conc.load(std::memory_order_relaxed) != 0; }
-constexpr int AUX_GROUPS = 8, AUX_PER_GROUP = 3, AUX_STREAMS = AUX_GROUPS * AUX_PER_GROUP, MAX_DEVICES = 16;
+constexpr int AUX_GROUPS = 32, AUX_PER_GROUP = 3, AUX_STREAMS = AUX_GROUPS * AUX_PER_GROUP, MAX_DEVICES = 16;
+static std::atomic<int> g_defer{0};
 struct AuxPool {
+    int pending[AUX_GROUPS] = {0};      // per group: aux streams with deferred (not yet joined) work
     bool ready = false;
     cudaStream_t st[AUX_STREAMS];
     cudaEvent_t fork_ev[AUX_STREAMS], join_ev[AUX_STREAMS];
@@ -56,7 +58,7 @@ static AuxPool *pool_for_current_device()
     return &p;
 }
 
-Branches::Branches(cudaStream_t main_stream) : main(main_stream), base(0), used(0), rc(BDETR_OK), on(concurrency_enabled())
+Branches::Branches(cudaStream_t main_stream) : main(main_stream), base(0), used(0), rc(BDETR_OK), on(concurrency_enabled()), shared(false)
 {
     if (!on) return;
     AuxPool *p = pool_for_current_device();
@@ -68,8 +70,8 @@ Branches::Branches(cudaStream_t main_stream) : main(main_stream), base(0), used(
     for (int i = 0; i < p->owners; ++i) if (p->owner[i] == main_stream) { g = i; break; }
     if (g < 0) {
         if (p->owners < AUX_GROUPS) { g = p->owners++; }
-        else { g = p->next; p->next = (p->next + 1) % AUX_GROUPS; }       // more caller streams than groups: share
-        p->owner[g] = main_stream;
+        else { g = p->next; p->next = (p->next + 1) % AUX_GROUPS; shared = true; }       // more caller streams than groups: share
+        if (!shared) p->owner[g] = main_stream;
     }
     base = g * AUX_PER_GROUP;
 }
@@ -86,6 +88,45 @@ cudaStream_t Branches::fork(int i)
     }
     used |= 1 << i;
     return p->st[k];
+}
+
+// Parameter-gradient side chains (weight gradients, bias / positional gradients) are only consumed at the end of the
+// step (optimizer / gradient all-reduce).  With bdetr_set_deferred_join(1) an entry point does not wait for them before
+// it returns: they keep running on their auxiliary streams and the CALLER orders its stream after them with
+// bdetr_join(stream) before it reads the gradients.  Everything else is joined inside the call as usual.
+int Branches::join_deferrable()
+{
+    if (!on) return rc;
+    if (g_defer.load(std::memory_order_relaxed) == 0 || shared) return join();      // (a shared group cannot track deferred work per caller)
+    AuxPool *p = pool_for_current_device();
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    p->pending[base / AUX_PER_GROUP] |= used;
+    used = 0;
+    return rc;
+}
+
+int join_pending(cudaStream_t main_stream)
+{
+    if (!concurrency_enabled()) return BDETR_OK;
+    AuxPool *p = pool_for_current_device();
+    if (!p) return BDETR_OK;
+    int g = -1, mask = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (int i = 0; i < p->owners; ++i) if (p->owner[i] == main_stream) { g = i; break; }
+        if (g < 0) return BDETR_OK;
+        mask = p->pending[g];
+        p->pending[g] = 0;
+    }
+    for (int i = 0; i < AUX_PER_GROUP; ++i) {
+        if (!(mask & (1 << i))) continue;
+        const int k = g * AUX_PER_GROUP + i;
+        if (cudaEventRecord(p->join_ev[k], p->st[k]) != cudaSuccess || cudaStreamWaitEvent(main_stream, p->join_ev[k], 0) != cudaSuccess) {
+            set_error("bdetr_join: %s", cudaGetErrorString(cudaGetLastError()));
+            return BDETR_E_CUDA;
+        }
+    }
+    return BDETR_OK;
 }
 
 int Branches::join()
@@ -107,6 +148,8 @@ int Branches::join()
 
 extern "C" __attribute__((visibility("default"))) int bdetr_set_concurrency(int on) { bdetr::g_conc.store(on ? 1 : 0); return BDETR_OK; }
 extern "C" __attribute__((visibility("default"))) int bdetr_get_concurrency(void) { return bdetr::g_conc.load(); }
+extern "C" __attribute__((visibility("default"))) int bdetr_set_deferred_join(int on) { bdetr::g_defer.store(on ? 1 : 0); return BDETR_OK; }
+extern "C" __attribute__((visibility("default"))) int bdetr_join(void *stream) { return bdetr::join_pending(reinterpret_cast<cudaStream_t>(stream)); }
 extern "C" __attribute__((visibility("default"))) int bdetr_version(void) { return 100; }
 extern "C" __attribute__((visibility("default"))) const char *bdetr_last_error(void) { return bdetr::g_err; }
 extern "C" __attribute__((visibility("default"))) int bdetr_set_mode(int mode)

@@ -511,5 +511,5 @@ API int bdetr_heads_bwd(int M, int D, int Dh, int C, int A, const float *x, cons
         g.C[0] = d_x;
         TRY(launch_gemm_umma_grouped(g, s));
     }
-    return br.join();
+    return br.join_deferrable();
 }

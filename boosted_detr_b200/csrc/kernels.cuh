@@ -20,11 +20,13 @@ struct Branches {
     explicit Branches(cudaStream_t main_stream);
     cudaStream_t fork(int i);       // aux stream i (0..2), ordered after everything enqueued on main so far
     int join();                     // main waits for every aux stream forked since the last join
+    int join_deferrable();          // the same, unless the caller asked to join parameter-gradient chains itself (bdetr_join)
     cudaStream_t main;
     int base, used, rc;
-    bool on;
+    bool on, shared;
 };
 bool concurrency_enabled();
+int join_pending(cudaStream_t main_stream);
 
 // C[M,N] = (beta ? C : 0) + op(A)[M,K] @ op(B)[K,N] (+bias[n]) ; act 1 = relu ;
 // relu_mask != NULL: C[m,n] = 0 where relu_mask[m*ldc+n] <= 0 (backward of relu, applied last).
@@ -112,6 +114,7 @@ int launch_batch_sum_acc(int B, int L, int D, const float *src, float *dst, cuda
 int launch_tile_rows(int B, int L, int D, const float *src, float *dst, int round_out, cudaStream_t s);
 int launch_round_tf32(size_t n, const float *src, float *dst, cudaStream_t s);
 int launch_accumulate(size_t n, const float *x, float *y, cudaStream_t s);
+int launch_suffix_sum(int n, size_t len, float *buf, cudaStream_t s);
 
 // acc: [2*Dh] scratch for the cross-CTA column sums
 int launch_bn_fwd(int M, int Dh, const float *h, const float *gamma, const float *beta, float *moving_mean,

@@ -345,6 +345,17 @@ __global__ void accumulate_kernel(size_t n, const float *__restrict__ x, float *
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) y[e] += x[e];
 }
 
+// buf is [n, len]: buf[i] += buf[i + 1] for i = n - 2 .. 0 (running gradient of the boosted running prediction:
+// block i's prediction feeds the losses of blocks i .. n - 1)
+__global__ void suffix_sum_kernel(int n, size_t len, float *__restrict__ buf)
+{
+    pdl_sync();
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < len; e += (size_t)gridDim.x * blockDim.x) {
+        float acc = buf[(size_t)(n - 1) * len + e];
+        for (int i = n - 2; i >= 0; --i) { acc += buf[(size_t)i * len + e]; buf[(size_t)i * len + e] = acc; }
+    }
+}
+
 static inline int ew_grid(size_t n) { size_t g = (n + 255) / 256; return (int)(g < 148 * 8 ? (g ? g : 1) : 148 * 8); }
 
 int launch_add_rows_fwd(int B, int L, int D, const float *x, const float *pos, float *out, int round_out, cudaStream_t s)
@@ -369,6 +380,13 @@ int launch_tile_rows(int B, int L, int D, const float *src, float *dst, int roun
     const size_t ld4 = (size_t)L * D / 4, n4 = ld4 * B;
     launch_k(tile_rows_kernel, ew_grid(n4), 256, 0, s, n4, ld4, (const float4 *)src, (float4 *)dst, round_out);
     BDETR_CHECK_LAUNCH("tile_rows_kernel");
+    return BDETR_OK;
+}
+int launch_suffix_sum(int n, size_t len, float *buf, cudaStream_t s)
+{
+    BDETR_REQUIRE(n > 0 && len > 0 && buf, BDETR_E_BAD_SHAPE, "bad suffix-sum arguments");
+    launch_k(suffix_sum_kernel, ew_grid(len), 256, 0, s, n, len, buf);
+    BDETR_CHECK_LAUNCH("suffix_sum_kernel");
     return BDETR_OK;
 }
 int launch_round_tf32(size_t n, const float *src, float *dst, cudaStream_t s)

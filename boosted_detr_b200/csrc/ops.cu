@@ -157,6 +157,10 @@ API int bdetr_accumulate(size_t n, const float *x, float *y, void *stream)
 {
     return launch_accumulate(n, x, y, as_stream(stream));
 }
+API int bdetr_suffix_sum(int n, size_t len, float *buf, void *stream)
+{
+    return launch_suffix_sum(n, len, buf, as_stream(stream));
+}
 API int bdetr_debug_force_attention_kernel(int which)
 {
     BDETR_REQUIRE((which >= 0 && which <= 2) || (which >= 20 && which <= 28), BDETR_E_UNSUPPORTED,

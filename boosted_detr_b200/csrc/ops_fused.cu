@@ -192,7 +192,7 @@ API int bdetr_attention_fused_bwd(int B, int Lq, int Lk, int D, int H, const flo
             TRY(proj_group_dgrad(Mk, D, 2, dY, Wm, nullptr, Mk, d_memory, (acc_flags >> 1) & 1, s));
         }
     }
-    return br.join();
+    return br.join_deferrable();
 }
 
 API int bdetr_ffn_fused_fwd(int M, int D, const float *x, const bdetr_ffn_params *w,
@@ -232,7 +232,7 @@ API int bdetr_ffn_fused_bwd(int M, int D, const float *x, const bdetr_ffn_params
     TRY(launch_gemm_umma_grouped(g, s));
     if (gw) TRY(launch_gemm(D, D, M, x, D, true, sc->d_h, D, false, nullptr, 0, nullptr, 1, 0, gw->w1, D, br.fork(1)));
     TRY(launch_gemm(M, D, D, sc->d_h, D, false, w->w1, D, true, nullptr, 0, nullptr, 1, 0, d_x, D, s));
-    return br.join();
+    return br.join_deferrable();
 }
 
 API int bdetr_decoder_self_fwd(int B, int Q, int D, int H, const float *q0, const float *q0_tc, const bdetr_attn_params *w,
@@ -307,5 +307,5 @@ API int bdetr_decoder_self_bwd(int B, int Q, int D, int H, const float *q0, cons
         TRY(launch_batch_reduce(cb, ws));
     }
     if (d_q0) TRY(proj_group_dgrad(Q, D, 3, dY, Wm, S_r, Q, d_q0, 1, s));     // d_q0 += S_r + sum_g dY[g] W[g]^T
-    return br.join();
+    return br.join_deferrable();
 }

@@ -52,6 +52,13 @@ int bdetr_set_pdl(int on);
  * stream before the call returns; CUDA-graph capturable. */
 int bdetr_set_concurrency(int on);
 int bdetr_get_concurrency(void);
+/* Deferred joins (off by default).  The fused backward entry points run their parameter-gradient side chains (weight
+ * gradients, bias / positional gradients) on auxiliary streams.  With deferred joins on, an entry point returns without
+ * ordering the caller's stream after those chains -- nothing inside the step reads parameter gradients -- and the
+ * caller issues bdetr_join(stream) once, before it hands the gradients to the optimizer / all-reduce.  Data gradients
+ * and everything the forward produces are always joined inside the call. */
+int bdetr_set_deferred_join(int on);
+int bdetr_join(void *stream);
 int bdetr_get_pdl(void);
 /* Number of kernels launched by this library since the last reset (bench.py's gpu_launches). */
 long long bdetr_launch_count(void);
@@ -217,6 +224,9 @@ int bdetr_add_positional_bwd(int B, int L, int D, const float *d_out, float *d_p
 int bdetr_tile_queries_fwd(int B, int Q, int D, const float *q0, float *out, void *stream);
 /* y += x elementwise (gradient joins). */
 int bdetr_accumulate(size_t n, const float *x, float *y, void *stream);
+/* buf [n,len]: buf[i] += buf[i+1] for i = n-2 .. 0.  The boosted running prediction of block i feeds the losses of blocks
+ * i .. n-1 (boosted_model.py:222-246), so its gradient is the suffix sum of the per-block loss gradients. */
+int bdetr_suffix_sum(int n, size_t len, float *buf, void *stream);
 /* dst = round-to-nearest tf32(src) (may alias).  Tensor-core mode keeps tf32-rounded shadows of the Dense
  * kernels and of the input features so that tcgen05's operand truncation is exact. */
 int bdetr_round_tf32(size_t n, const float *src, float *dst, void *stream);
