@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libbdetr.so")
 
 BDETR_OK = 0
 BDETR_E_BAD_SHAPE, BDETR_E_CUDA, BDETR_E_INVALID_COST, BDETR_E_INFEASIBLE, BDETR_E_NULL, BDETR_E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
+BDETR_E_NCCL = -7
 MODE_FP32, MODE_TF32 = 0, 1
 
 
@@ -89,6 +90,12 @@ PROTOTYPES = {
     "bdetr_head_fwd": (c_int, [I, I, I, I, I, I, F, P, POINTER(HeadParams), F, F, P, I, POINTER(HeadSaved), P]),
     "bdetr_head_bwd": (c_int, [I, I, I, I, I, I, F, P, POINTER(HeadParams), F, POINTER(HeadSaved), P, P, I,
                                POINTER(HeadParams), POINTER(HeadScratch), P]),
+    "bdetr_comm_unique_id": (c_int, [P]),
+    "bdetr_comm_init": (c_int, [POINTER(c_void_p), I, I, P]),
+    "bdetr_comm_destroy": (c_int, [P]),
+    "bdetr_comm_info": (c_int, [P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "bdetr_allreduce": (c_int, [P, P, c_size_t, P]),
+    "bdetr_broadcast": (c_int, [P, P, c_size_t, I, P]),
     "bdetr_gemm": (c_int, [I, I, I, P, I, P, I, P, I, I, P, P]),
     "bdetr_pos_projection": (c_int, [I, I, P, I, POINTER(PTR3), POINTER(PTR3), POINTER(PTR3), P]),
     "bdetr_attention_fused_fwd": (c_int, [I, I, I, I, I, P, P, POINTER(PosFold), POINTER(AttnParams), F, c_uint32, P, F, I, P,

@@ -806,11 +806,22 @@ class BoostedDETR:
         y_pred, ctx = self.forward(feats, y_true, True)
         self.last_ctx_train, self.last_preds = ctx, y_pred
         m = self._collect_metrics(ctx)
-        self.backward(ctx, gscale=1.0 / self.num_replicas)
+        pipe = getattr(self, "bucket_pipeline", None)
+        in_hook = self.optimizer is not None and pipe is not None and pipe.bucket_optimizer and ctx.get("fused")
+        if in_hook:                               # the update runs bucket by bucket behind each block's all-reduce
+            self.optimizer._ensure_bucket_tables(self)
+            pipe.opt_lr = (self.optimizer.current_lr(), None)
+        try:
+            self.backward(ctx, gscale=1.0 / self.num_replicas)
+        finally:
+            if pipe is not None:
+                lr_used, pipe.opt_lr = pipe.opt_lr, None
         self._join_metrics()
         if self.grad_allreduce is not None:
             self.grad_allreduce(self._flat[1])
-        if self.optimizer is not None:
+        if in_hook:
+            self.optimizer.finish_step(lr_used[0])
+        elif self.optimizer is not None:
             self.optimizer.apply(self)
         self.step_count += 1
         self.advance_dropout_seed()

@@ -55,7 +55,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [nvcc, "-shared", "-o", LIB, *objs]      # static cudart; no libcuda dependency (driver API via the runtime)
+    link = [nvcc, "-shared", "-o", LIB, *objs, "-ldl"]      # static cudart; no libcuda / libnccl dependency (driver API via the runtime, NCCL via dlopen)
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

@@ -5,6 +5,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .device import ptr
 from .losses_and_metrics import raise_for_status
 
 
@@ -46,14 +47,23 @@ class GraphedTrainStep:
         y_true = [s["category"], s["attribute"], s["bbox"], s["num_objects"]]
         _, ctx = m.forward(s["features"], y_true, True)
         metrics = m._collect_metrics(ctx)
-        m.backward(ctx, gscale=1.0 / m.num_replicas)
+        pipe = getattr(m, "bucket_pipeline", None)
+        # the optimizer update belongs to the graph whenever the gradients are final inside it (single GPU, or the
+        # bucketed all-reduce); its learning rate is read from device memory (see SGD.capture / pre_replay).  With a
+        # bucket pipeline the update of block i's variables is queued right behind that block's all-reduce.
+        self.optimizer_in_graph = m.optimizer is not None and (m.grad_allreduce is None or m.grad_bucket_hook is not None)
+        self.optimizer_in_hook = bool(self.optimizer_in_graph and pipe is not None and pipe.bucket_optimizer and ctx.get("fused"))
+        if self.optimizer_in_hook:
+            pipe.opt_lr = (0.0, ptr(m.optimizer._lr_dev)) if capturing else None
+        try:
+            m.backward(ctx, gscale=1.0 / m.num_replicas)
+        finally:
+            if pipe is not None:
+                pipe.opt_lr = None
         m._join_metrics()
         if m.grad_bucket_hook is not None and m.grad_allreduce is not None:
             m.grad_allreduce(m._flat[1])          # joins the bucketed all-reduces issued inside the backward (captured too)
-        # the optimizer update belongs to the graph whenever the gradients are final inside it (single GPU, or the
-        # bucketed all-reduce above); its learning rate is read from device memory (see SGD.capture / pre_replay)
-        self.optimizer_in_graph = m.optimizer is not None and (m.grad_allreduce is None or m.grad_bucket_hook is not None)
-        if self.optimizer_in_graph and capturing:
+        if self.optimizer_in_graph and capturing and not self.optimizer_in_hook:
             m.optimizer.capture(m)
         return metrics, m.status_all
 

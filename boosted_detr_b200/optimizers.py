@@ -9,6 +9,7 @@ chunk table, so they are neither clipped nor updated).  The update itself is bde
 """
 from __future__ import annotations
 
+import ctypes
 import math
 
 import numpy as np
@@ -113,6 +114,46 @@ class SGD:
                   ptr(self._accum), ptr(self._partial), lr, lr_dev, self.momentum, int(self.nesterov),
                   0.0 if self.clipnorm is None else self.clipnorm, stream_ptr())
 
+    # -- per-bucket form: the update of boosted block i's variables right behind its gradient all-reduce -------------
+    def _ensure_bucket_tables(self, model):
+        """One chunk table per gradient bucket (model._buckets: contiguous ranges of the flat buffers, one per boosted
+        block in backward order), so the clip + update of a block can be queued as soon as its gradients are final
+        (the optimizer step fused behind the all-reduce epilogue) instead of after the whole backward."""
+        from .layers import Layer
+        self._ensure_table(model)
+        key = (id(model._flat[0]), Layer.trainable_epoch)
+        if getattr(self, "_btab_key", None) == key:
+            return
+        slots = self.trainable_slots(model)
+        tabs, counts = [], []
+        for _, lo, hi in model._buckets:
+            t = self.chunk_table([sl for sl in slots if lo <= sl[1] < hi])
+            tabs.append(t)
+            counts.append(len(t))
+        dev = model._flat[0].device
+        allt = np.concatenate(tabs) if sum(counts) else np.zeros(0, dtype=tabs[0].dtype)
+        self._btable = torch.from_numpy(allt.view(np.uint8).copy()).to(dev) if len(allt) else torch.zeros(32, dtype=torch.uint8, device=dev)
+        self._bpartial = zeros(max(1, len(allt)))
+        self._bcounts = counts
+        self._bfirst = [int(x) for x in np.concatenate([[0], np.cumsum(counts)[:-1]])]
+        self._btab_key = key
+
+    def launch_bucket(self, model, bucket_index, lr=0.0, lr_dev=None):
+        """Clip + update of the variables of gradient bucket `bucket_index` on the current stream."""
+        n, first = self._bcounts[bucket_index], self._bfirst[bucket_index]
+        if n == 0:
+            return
+        rec = 24                                                  # sizeof(bdetr_opt_chunk)
+        tab = ctypes.c_void_p(self._btable.data_ptr() + first * rec)
+        part = ctypes.c_void_p(self._bpartial.data_ptr() + first * 4)
+        _lib.call("bdetr_sgd_step", n, tab, ptr(model._flat[0]), ptr(model._flat[1]), ptr(self._accum), part, lr, lr_dev,
+                  self.momentum, int(self.nesterov), 0.0 if self.clipnorm is None else self.clipnorm, stream_ptr())
+
+    def finish_step(self, lr):
+        """Book-keeping of a step whose update ran bucket by bucket."""
+        self.iterations += 1
+        self.last_lr = lr
+
     def apply(self, model):
         """One optimizer step on model's flat buffers with the gradients currently in them (after any all-reduce)."""
         if model._flat is None:
@@ -127,6 +168,7 @@ class SGD:
     def prepare(self, model):
         """Allocations and host->device copies of the chunk table: must happen OUTSIDE graph capture."""
         self._ensure_table(model)
+        self._ensure_bucket_tables(model)
         if getattr(self, "_lr_dev", None) is None:
             self._lr_dev = zeros(1)
             self._lr_host = torch.zeros(16, dtype=torch.float32).pin_memory()    # ring: the host may run a few steps ahead

@@ -43,16 +43,72 @@ def shard_batch(inputs: dict, rank: int, world: int) -> dict:
     return out
 
 
+class Comm:
+    """bdetr_comm: the NCCL communicator behind the C ABI (csrc/comm.cu).  torch.distributed is only the out-of-band
+    channel that hands rank 0's 128-byte NCCL unique id to the other ranks; the gradient bytes never touch it."""
+
+    def __init__(self):
+        import ctypes
+        from . import _lib
+        assert dist.is_initialized()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        idbuf = (ctypes.c_ubyte * 128)()
+        if self.rank == 0:
+            _lib.call("bdetr_comm_unique_id", idbuf)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        idbuf = (ctypes.c_ubyte * 128)(*t.cpu().tolist())
+        self.handle = ctypes.c_void_p()
+        _lib.call("bdetr_comm_init", ctypes.byref(self.handle), self.rank, self.world, idbuf)
+        ver = ctypes.c_int(0)
+        _lib.call("bdetr_comm_info", self.handle, None, None, ctypes.byref(ver))
+        self.nccl_version = ver.value
+
+    def allreduce(self, t: torch.Tensor):
+        from . import _lib
+        from .device import ptr, stream_ptr
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        _lib.call("bdetr_allreduce", self.handle, ptr(t), t.numel(), stream_ptr())
+
+    def broadcast(self, t: torch.Tensor, root=0):
+        from . import _lib
+        from .device import ptr, stream_ptr
+        _lib.call("bdetr_broadcast", self.handle, ptr(t), t.numel(), root, stream_ptr())
+
+
+_comm = None
+
+
+def get_comm():
+    """The process's bdetr_comm (created on first use; needs torch.distributed initialised and a CUDA device)."""
+    global _comm
+    if _comm is None and dist.is_initialized() and dist.get_world_size() > 1 and torch.cuda.is_available() \
+            and os.environ.get("BDETR_COMM", "abi") == "abi":
+        _comm = Comm()
+    return _comm
+
+
 def allreduce_gradients(flat_grads: torch.Tensor):
-    """Sum of the per-replica gradients (each already scaled by 1/replicas): the only collective on the path."""
+    """Sum of the per-replica gradients (each already scaled by 1/replicas): the only collective on the path.  CUDA
+    buffers go through bdetr_allreduce (ncclAllReduce behind the C ABI); host tensors (the gloo tests) through
+    torch.distributed."""
     if dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+        comm = get_comm() if flat_grads.is_cuda else None
+        if comm is not None:
+            comm.allreduce(flat_grads)
+        else:
+            dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
     return flat_grads
 
 
 def broadcast_tensor(t: torch.Tensor, src: int = 0):
     if dist.is_initialized() and dist.get_world_size() > 1:
-        dist.broadcast(t, src=src)
+        comm = get_comm() if t.is_cuda else None
+        if comm is not None and t.dtype == torch.float32 and t.is_contiguous():
+            comm.broadcast(t, src)
+        else:
+            dist.broadcast(t, src=src)
     return t
 
 
@@ -66,16 +122,24 @@ class DataParallel:
     exposed.  The collectives are issued in the same order on every rank and are captured into the CUDA graph of
     the step together with the kernels.  overlap=False: one all-reduce of the whole buffer after the backward."""
 
-    def __init__(self, model, overlap=True):
+    def __init__(self, model, overlap=True, bucket_optimizer=True):
         self.model = model
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.overlap = overlap and self.world > 1
         self.comm_stream = None
+        self.opt_lr = None                # (lr, lr_dev) of the running step when the update runs bucket by bucket
         model.num_replicas = self.world
         if self.world > 1:
             model.grad_allreduce = self.finish
             if self.overlap:
                 model.grad_bucket_hook = self.reduce_bucket
+        elif bucket_optimizer:
+            # one GPU: nothing to reduce, but the per-bucket optimizer update still leaves the critical path
+            model.grad_allreduce = self.finish
+            model.grad_bucket_hook = self.reduce_bucket
+            self.overlap = True
+        self.bucket_optimizer = bucket_optimizer and self.overlap
+        model.bucket_pipeline = self
         self.broadcast_weights()
 
     def _comm(self):
@@ -91,13 +155,19 @@ class DataParallel:
         for ev in events:
             comm.wait_event(ev)
         with torch.cuda.stream(comm):
-            allreduce_gradients(self.model._flat[1][lo:hi])
+            if self.world > 1:
+                allreduce_gradients(self.model._flat[1][lo:hi])
+            # clip + SGD update of this block's variables right behind its all-reduce
+            if self.opt_lr is not None:
+                m = self.model
+                bi = next(k for k, (b, _, _) in enumerate(m._buckets) if b == block)
+                m.optimizer.launch_bucket(m, bi, self.opt_lr[0], self.opt_lr[1])
 
     def finish(self, flat_grads: torch.Tensor):
         """Called at the end of the backward: joins the bucketed all-reduces, or does the single one."""
         if self.overlap:
             torch.cuda.current_stream().wait_stream(self._comm())
-        else:
+        elif self.world > 1:
             allreduce_gradients(flat_grads)
 
     # kept for callers that drive the collective themselves

@@ -31,7 +31,8 @@ typedef enum {
     BDETR_E_INVALID_COST = -3, /* scipy: ValueError("matrix contains invalid numeric entries") */
     BDETR_E_INFEASIBLE = -4,   /* scipy: ValueError("cost matrix is infeasible")               */
     BDETR_E_NULL = -5,
-    BDETR_E_UNSUPPORTED = -6
+    BDETR_E_UNSUPPORTED = -6,
+    BDETR_E_NCCL = -7          /* an NCCL call failed / libnccl could not be loaded (bdetr_last_error has the text) */
 } bdetr_status;
 
 /* compute modes for the dense (GEMM / attention) kernels */
@@ -414,6 +415,22 @@ typedef struct {
 int bdetr_sgd_step(int n_chunks, const bdetr_opt_chunk *chunks,
                    float *weights, const float *grads, float *accum, float *partial,
                    float lr, const float *lr_dev, float momentum, int nesterov, float clipnorm, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data parallel: the gradient all-reduce, the only collective on the path.  The reference's
+ * tf.distribute.MirroredStrategy (parameters.py:74) sums the replica gradients with TF-internal NCCL; here one NCCL
+ * communicator per device lives behind an opaque bdetr_comm (libnccl bound at run time with dlopen).
+ *   rank 0:      bdetr_comm_unique_id(id)  -> hand the 128 bytes to every rank by any out-of-band channel
+ *   every rank:  cudaSetDevice(local) ; bdetr_comm_init(&comm, rank, world, id)
+ *   per step:    bdetr_allreduce(comm, flat_grads + lo, hi - lo, stream)   in-place sum, stream-ordered, graph capturable
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bdetr_comm bdetr_comm;
+int bdetr_comm_unique_id(void *id128);
+int bdetr_comm_init(bdetr_comm **comm, int rank, int world, const void *id128);
+int bdetr_comm_destroy(bdetr_comm *comm);
+int bdetr_comm_info(const bdetr_comm *comm, int *rank, int *world, int *nccl_version);
+int bdetr_allreduce(bdetr_comm *comm, float *buf, size_t count, void *stream);
+int bdetr_broadcast(bdetr_comm *comm, float *buf, size_t count, int root, void *stream);
 
 #ifdef __cplusplus
 }
