@@ -90,6 +90,14 @@ PROTOTYPES = {
     "bdetr_head_fwd": (c_int, [I, I, I, I, I, I, F, P, POINTER(HeadParams), F, F, P, I, POINTER(HeadSaved), P]),
     "bdetr_head_bwd": (c_int, [I, I, I, I, I, I, F, P, POINTER(HeadParams), F, POINTER(HeadSaved), P, P, I,
                                POINTER(HeadParams), POINTER(HeadScratch), P]),
+    "bdetr_pairwise_iou": (c_int, [I, I, I, P, P, P, P, P]),
+    "bdetr_attention_block_saved_bytes": (c_size_t, [I, I, I, I, I, I]),
+    "bdetr_attention_block_scratch_bytes": (c_size_t, [I, I, I, I, I]),
+    "bdetr_ffn_block_saved_bytes": (c_size_t, [I, I, I]),
+    "bdetr_ffn_block_scratch_bytes": (c_size_t, [I, I]),
+    "bdetr_heads_saved_bytes": (c_size_t, [I, I, I, I]),
+    "bdetr_heads_scratch_bytes": (c_size_t, [I, I, I, I]),
+    "bdetr_inverse_tokenize": (c_int, [I, I, I, I, P, P, P, P, P, P, F, P]),
     "bdetr_comm_unique_id": (c_int, [P]),
     "bdetr_comm_init": (c_int, [POINTER(c_void_p), I, I, P]),
     "bdetr_comm_destroy": (c_int, [P]),

@@ -75,6 +75,11 @@ class BoostedDETR:
                                     attribute_weight=attribute_weight, exist_weight=None, name="MatchingLoss")
         self.optimizer = None
         self.dropout_seed = None          # None: dropout off (parity runs); int: hash-mask dropout, rate .1
+        # Inference early exit (the reference's TODO, README.md:9): stop after the first boosted block (>= min blocks)
+        # at which EVERY image's least confident query reaches the threshold; None = run all blocks.
+        self.early_exit_threshold = None
+        self.early_exit_min_blocks = 1
+        self.last_exit_block = None
         self.step_count = 0
         self.num_replicas = 1
         self.grad_allreduce = None        # set by parallel.DataParallel (joins / performs the gradient all-reduce)
@@ -162,6 +167,18 @@ class BoostedDETR:
         for n, o, k in self.named_weights():
             if n in d:
                 o._weights[k].copy_(torch.from_numpy(np.ascontiguousarray(d[n], np.float32)).to(o._weights[k].device))
+
+    def save_weights(self, path, naming="keras"):
+        """Keras `Model.save_weights` by variable name (checkpoint.py: .npz, layer-name or TF object-graph keys)."""
+        from .checkpoint import save_weights
+        return save_weights(self, path, naming)
+
+    def load_weights(self, source, strict=True):
+        """Keras `Model.load_weights` (reference notebook cell 26) from an exported checkpoint (checkpoint.py)."""
+        from .checkpoint import load_weights
+        if self._flat is None:
+            self.build()
+        return load_weights(self, source, strict)
 
     def get_grads_dict(self):
         return {n: o._grads[k].detach().cpu().numpy().copy() for n, o, k in self.named_weights() if k in o._grads}
@@ -309,6 +326,25 @@ class BoostedDETR:
         ev.record(stream if stream is not None else torch.cuda.current_stream())
         tr.append((label, ev))
 
+    # -- inference early exit ---------------------------------------------------------------------
+    def _early_exit(self, i, cums):
+        """True when inference may stop after boosted block i.  Confidence of a query = max class probability of the
+        running prediction / (i + 2) (the running prediction after block i is a sum of i + 2 softmax vectors: block 0
+        counts twice, quirk Q2); an image is confident when its least confident query is.  One 4*B-byte D2H + sync."""
+        if self.early_exit_threshold is None or i + 1 < self.early_exit_min_blocks or i + 1 >= self.num_decoder_blocks:
+            return False
+        cat, attr = cums[0], cums[1]
+        B, Q, C = cat.shape
+        conf, iconf = empty(B, Q), empty(B)
+        _lib.call("bdetr_inverse_tokenize", B, Q, C, attr.shape[-1], ptr(cat), None, None, None, ptr(conf), ptr(iconf),
+                  1.0 / (i + 2), stream_ptr())
+        if getattr(self, "_exit_host", None) is None or self._exit_host.numel() != B:
+            self._exit_host = torch.empty(B, dtype=torch.float32).pin_memory()
+        self._exit_host.copy_(iconf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.last_image_confidence = self._exit_host.clone()
+        return bool((self._exit_host >= self.early_exit_threshold).all())
+
     # -- fused tensor-core path -------------------------------------------------------------------
     def _use_fused(self, feats):
         """Tensor-core mode, model width 256, every layer already built (the very first call builds the layers lazily
@@ -417,6 +453,9 @@ class BoostedDETR:
                 if training:
                     loss_ctxs.append(self.loss_fn.forward(y_true, cums, prepared))
                     self._mark(f"fwd loss{i} done (side)")
+                self.last_exit_block = i
+                if not training and self._early_exit(i, cums):
+                    break
         for bs in bstreams:
             main.wait_stream(bs)
         main.wait_stream(pre_s)
@@ -656,6 +695,9 @@ class BoostedDETR:
                 self._mark(f"fwd heads{i} done (dec)")
                 cums = new_cums
                 blocks.append({"enc": c_enc, "prep": c_prep, "dec": c_dec, "heads": c_heads})
+                self.last_exit_block = i
+                if not training and self._early_exit(i, cums):
+                    break
                 if training:
                     ls = loss_streams[i]
                     ls.wait_stream(dec_s)
@@ -850,6 +892,9 @@ class BoostedDETR:
         return history
 
     def predict_indices(self, inputs):
-        """Numeric half of InverseTokenization (argmax category, attribute >= 0.5) — reference tokenizers.py:130-135."""
+        """Numeric half of InverseTokenization (reference tokenizers.py:130-135) on the device: (category tokens [B,Q,1],
+        attribute tokens [B,Q,A] = multi-hot * arange(A), boxes)."""
+        from .tokenizers import InverseTokenization
         cat, attr, box = self.call(inputs, training=False)
-        return cat.argmax(dim=-1), attr >= 0.5, box
+        tok_c, tok_a = InverseTokenization(self.vocab_dict).tokens([cat, attr])
+        return tok_c, tok_a, box

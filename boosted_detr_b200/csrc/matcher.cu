@@ -1181,6 +1181,37 @@ extern "C" __attribute__((visibility("default"))) int bdetr_cost_matrix_prepared
     return BDETR_OK;
 }
 
+// MatchingMetric.call (losses_and_metrics.py:176-192): pairwise IoU [B,T,Q] of COCO boxes (targets = rows), times the
+// assignment mask when one is given.  IOU_Metric (:17-18) = 1 - tfa.giou_loss(mode='iou') = 1 - (1 - iou).
+__global__ void __launch_bounds__(256)
+pairwise_iou_kernel(int T, int Q, const float *__restrict__ box_true, const float *__restrict__ box_pred, const float *__restrict__ mask,
+                    float *__restrict__ out)
+{
+    pdl_sync();
+    const int b = blockIdx.y;
+    const size_t per = (size_t)T * Q;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(e / Q), q = (int)(e - (size_t)t * Q);
+        const float4 tb4 = reinterpret_cast<const float4 *>(box_true)[(size_t)b * T + t];
+        const float4 pb4 = reinterpret_cast<const float4 *>(box_pred)[(size_t)b * Q + q];
+        float iou_v;
+        (void)box_pair_cost(coco_to_tf(tb4.x, tb4.y, tb4.z, tb4.w), coco_to_tf(pb4.x, pb4.y, pb4.z, pb4.w), &iou_v);
+        const float v = 1.0f - (1.0f - iou_v);
+        out[(size_t)b * per + e] = mask ? mask[(size_t)b * per + e] * v : v;
+    }
+}
+
+extern "C" __attribute__((visibility("default"))) int bdetr_pairwise_iou(int B, int T, int Q, const float *box_true, const float *box_pred,
+                                    const float *mask, float *out, void *stream)
+{
+    BDETR_REQUIRE(B > 0 && T > 0 && Q > 0, BDETR_E_BAD_SHAPE, "B,T,Q must be positive");
+    BDETR_REQUIRE(box_true && box_pred && out, BDETR_E_NULL, "null pointer");
+    const int gx = (int)(((size_t)T * Q + 255) / 256);
+    launch_k(pairwise_iou_kernel, dim3(gx < 64 ? gx : 64, B), 256, 0, as_stream(stream), T, Q, box_true, box_pred, mask, out);
+    BDETR_CHECK_LAUNCH("pairwise_iou_kernel");
+    return BDETR_OK;
+}
+
 // Convenience form of the two calls above with a library-owned, grow-only scratch buffer for the prepared targets.
 // The buffer is allocated on first use / growth (do that outside CUDA-graph capture) and shared by all calls on the
 // device: NOT for concurrent use from several streams -- callers that overlap matchers (the model does) hold their own

@@ -309,3 +309,27 @@ API int bdetr_decoder_self_bwd(int B, int Q, int D, int H, const float *q0, cons
     if (d_q0) TRY(proj_group_dgrad(Q, D, 3, dY, Wm, S_r, Q, d_q0, 1, s));     // d_q0 += S_r + sum_g dY[g] W[g]^T
     return br.join_deferrable();
 }
+
+// ---- workspace queries (caller-owned buffers; see include/bdetr.h) ------------------------------------------------------
+API size_t bdetr_attention_block_saved_bytes(int B, int Lq, int Lk, int D, int H, int training)
+{
+    const size_t q = (size_t)B * Lq * D, k = (size_t)B * Lk * D;
+    return 4 * (q + 2 * k + q /* o */ + (size_t)B * H * Lq /* lse */ + (training ? q : 0) /* z */ + 2 * (size_t)B * Lq /* mean, rstd */);
+}
+API size_t bdetr_attention_block_scratch_bytes(int B, int Lq, int Lk, int D, int H)
+{
+    const size_t q = (size_t)B * Lq * D, k = (size_t)B * Lk * D;
+    const size_t L = (size_t)(Lq > Lk ? Lq : Lk);
+    return 4 * (q + 2 * k /* d_qp, d_kp, d_vp */ + q /* d_o */ + q /* d_z */ + (size_t)B * H * Lq /* delta */ + q /* d_resid */ + 4 * L * D /* sums */);
+}
+API size_t bdetr_ffn_block_saved_bytes(int M, int D, int training) { return 4 * ((size_t)M * D * (training ? 2 : 1) + 2 * (size_t)M); }
+API size_t bdetr_ffn_block_scratch_bytes(int M, int D) { return 4 * 2 * (size_t)M * D; }
+API size_t bdetr_heads_saved_bytes(int M, int Dh, int C, int A)
+{
+    return 4 * (3 * (size_t)M * Dh + 4 * 3 * (size_t)Dh + (size_t)((M + 127) / 128) * 2 * 3 * Dh + (size_t)M * (C + A + 4));
+}
+API size_t bdetr_heads_scratch_bytes(int M, int Dh, int C, int A)
+{
+    const size_t n = (size_t)C + A + 4;
+    return 4 * ((size_t)M * n + (size_t)Dh * n + n + 2 * 3 * (size_t)Dh + 3 * (size_t)M * Dh);
+}

@@ -18,17 +18,31 @@ DEFAULT_ATTRIBUTE_WEIGHT = 100.0
 DEFAULT_EXIST_WEIGHT = 100.0
 
 
-# Markers with the reference's function names: CostArray.call(y_true, y_pred, func) selects the term.
-def CategoryLoss(*_):  # reference :44-49
-    raise TypeError("CategoryLoss is evaluated on device through CostArray / MatchingLoss")
+# The reference's loss functions (:44-72) are elementwise over broadcast shapes and are only ever evaluated through
+# CostArray.call(y_true, y_pred, func), which builds [B,T,1,K] x [B,1,Q,K] operands.  Here they are callable markers:
+# CostArray selects the term by identity, and a direct call evaluates the same pairwise [B,T,Q] cost on the device --
+# with either the reference's broadcast operands ([B,T,1,K], [B,1,Q,K]) or the plain ([B,T,K], [B,Q,K]) pair.
+def _pairwise_call(func, y_true, y_pred):
+    yt, yp = f32(y_true), f32(y_pred)
+    if yt.dim() == 4 and yt.shape[2] == 1:
+        yt = yt[:, :, 0, :].contiguous()
+    if yp.dim() == 4 and yp.shape[1] == 1:
+        yp = yp[:, 0, :, :].contiguous()
+    if yt.dim() != 3 or yp.dim() != 3:
+        raise ValueError("expected [B,T,K] / [B,Q,K] (or the reference's [B,T,1,K] / [B,1,Q,K]) operands")
+    return CostArray().call(yt, yp, func)
 
 
-def AttributeLoss(*_):  # reference :51-57
-    raise TypeError("AttributeLoss is evaluated on device through CostArray / MatchingLoss")
+def CategoryLoss(y_true, y_pred):  # reference :44-49
+    return _pairwise_call(CategoryLoss, y_true, y_pred)
 
 
-def BoxLoss(*_):  # reference :68-72
-    raise TypeError("BoxLoss is evaluated on device through CostArray / MatchingLoss")
+def AttributeLoss(y_true, y_pred):  # reference :51-57
+    return _pairwise_call(AttributeLoss, y_true, y_pred)
+
+
+def BoxLoss(y_true, y_pred):  # reference :68-72
+    return _pairwise_call(BoxLoss, y_true, y_pred)
 
 
 def raise_for_status(status: torch.Tensor) -> None:
@@ -207,5 +221,13 @@ class MatchingMetric:
         self.name = name
 
     def call(self, inputs, assignment_mask=None):
-        raise NotImplementedError(
-            "the IOU metric is produced by MatchingLoss.call (fused into the matched-loss kernel)")
+        """inputs = [bbox_true [B,T,4], bbox_pred [B,Q,4]] (COCO x,y,w,h) -> mask * pairwise IoU [B,T,Q] (reference :187-188).
+        MatchingLoss.call produces the reduced `IOU` metric itself (fused into the matched-loss kernel)."""
+        box_true, box_pred = (f32(t) for t in inputs)
+        B, T, Q = box_true.shape[0], box_true.shape[1], box_pred.shape[1]
+        out = empty(B, T, Q)
+        m = None if assignment_mask is None else f32(assignment_mask)
+        _lib.call("bdetr_pairwise_iou", B, T, Q, ptr(box_true), ptr(box_pred), ptr(m), ptr(out), stream_ptr())
+        return out
+
+    __call__ = call

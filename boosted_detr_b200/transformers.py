@@ -45,8 +45,38 @@ class MultiheadAttention(Layer):
             self.add_weight(f"{nm}/kernel", glorot_normal(rng, fi, fo))
             self.add_weight(f"{nm}/bias", np.zeros(fo, np.float32))
 
-    def forward(self, inputs, training=False):
-        raise NotImplementedError("MultiheadAttention runs fused inside AttentionBlock (bdetr_attention_block_fwd)")
+    def forward(self, inputs, training=False, attention_mask=None):
+        """Stand-alone MultiheadAttention.call (reference :68-102), inference only: the three projections, the attention
+        core and the output projection through bdetr_gemm / bdetr_attention_core_fwd.  Inside the model the layer runs
+        fused in AttentionBlock's entry points (which also provide the backward).  `attention_mask` multiplies the
+        probabilities AFTER the softmax in the reference (:92-94) and is all ones on this path: only None is accepted."""
+        if attention_mask is not None:
+            raise NotImplementedError("attention_mask is always ones on the reference's path; pass None")
+        query, key, value = (f32(t) for t in inputs)
+        self.maybe_build([query, key, value])
+        B, Lq, D = query.shape
+        Lk, H, d = key.shape[1], self.num_attention_heads, self.dim
+        P = H * d
+        w, _ = self.gemm_weights()
+        rnd = 1 if _lib.load().bdetr_get_mode() == _lib.MODE_TF32 else 0
+
+        def dense(x, nm, rows, n_in, n_out):
+            y = empty(rows, n_out)
+            _lib.call("bdetr_gemm", rows, n_out, n_in, ptr(x), 0, ptr(w[f"{nm}/kernel"]), 0, ptr(self._weights[f"{nm}/bias"]), 0, 0,
+                      ptr(y), stream_ptr())
+            if rnd:
+                _lib.call("bdetr_round_tf32", y.numel(), ptr(y), ptr(y), stream_ptr())
+            return y
+        qp = dense(query, "QueryProjection", B * Lq, D, P)
+        kp = dense(key, "KeyProjection", B * Lk, key.shape[-1], P)
+        vp = dense(value, "ValueProjection", B * Lk, value.shape[-1], P)
+        o, lse = empty(B, H, Lq, d), empty(B, H, Lq)
+        _lib.call("bdetr_attention_core_fwd", B, H, Lq, Lk, d, ptr(qp), ptr(kp), ptr(vp), ptr(o), ptr(lse), stream_ptr())
+        out = empty(B, Lq, w["OutputProjection/kernel"].shape[1])
+        # [B,H,Lq,d] re-read as [B*Lq, H*d] without a permute (reference :100, quirk Q1)
+        _lib.call("bdetr_gemm", B * Lq, out.shape[-1], P, ptr(o), 0, ptr(w["OutputProjection/kernel"]), 0,
+                  ptr(self._weights["OutputProjection/bias"]), 0, 0, ptr(out), stream_ptr())
+        return out, {"qp": qp, "kp": kp, "vp": vp, "o": o, "lse": lse}
 
 
 class AttentionBlock(Layer):

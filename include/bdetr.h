@@ -136,6 +136,21 @@ int bdetr_matched_loss_bwd(int B, int T, int Q, int C, int A,
                            float w_cat, float w_box, float w_attr, float w_exist, float gscale,
                            float *d_cat_pred, float *d_attr_pred, float *d_box_pred, void *stream);
 
+/* MatchingMetric.call (:176-192): out [B,T,Q] = (mask ? mask : 1) * IoU(box_true[b,t], box_pred[b,q]) on COCO x,y,w,h boxes
+ * (IOU_Metric :17-18).  mask may be NULL. */
+int bdetr_pairwise_iou(int B, int T, int Q, const float *box_true, const float *box_pred, const float *mask, float *out,
+                       void *stream);
+
+/* Caller-owned buffers of the layer-level entry points, in bytes (no hidden allocation: the caller sizes `saved` /
+ * `scratch` from these).  Each returns the total over the buffers of the corresponding struct, laid out as the struct's
+ * comments state (fp32).  training = 0: what an inference call needs. */
+size_t bdetr_attention_block_saved_bytes(int B, int Lq, int Lk, int D, int H, int training);
+size_t bdetr_attention_block_scratch_bytes(int B, int Lq, int Lk, int D, int H);   /* bdetr_attn_scratch + d_resid + sums of the fused form */
+size_t bdetr_ffn_block_saved_bytes(int M, int D, int training);
+size_t bdetr_ffn_block_scratch_bytes(int M, int D);
+size_t bdetr_heads_saved_bytes(int M, int Dh, int C, int A);
+size_t bdetr_heads_scratch_bytes(int M, int Dh, int C, int A);
+
 /* ------------------------------------------------------------------------------------------
  * Dense path (K1-K6)
  * ---------------------------------------------------------------------------------------- */
@@ -415,6 +430,18 @@ typedef struct {
 int bdetr_sgd_step(int n_chunks, const bdetr_opt_chunk *chunks,
                    float *weights, const float *grads, float *accum, float *partial,
                    float lr, const float *lr_dev, float momentum, int nesterov, float clipnorm, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Inference tail: the numeric half of InverseTokenization.call (tokenizers.py:126-137) and the
+ * confidence statistic of the early-exit path the reference lists as TODO (README.md:9).
+ *   tokens_categories [B,Q] int32 = argmax_c cat_pred (first maximum, like tf.argmax)
+ *   tokens_attributes [B,Q,A] int32 = (attr_pred >= .5) * arange(A)
+ *   confidence [B,Q] = conf_scale * max_c cat_pred ; image_confidence [B] = min_q confidence
+ * Any output may be NULL (image_confidence needs confidence).  conf_scale = 1 / (number of summed softmax vectors).
+ * ---------------------------------------------------------------------------------------- */
+int bdetr_inverse_tokenize(int B, int Q, int C, int A, const float *cat_pred, const float *attr_pred,
+                           int32_t *tokens_categories, int32_t *tokens_attributes, float *confidence,
+                           float *image_confidence, float conf_scale, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Data parallel: the gradient all-reduce, the only collective on the path.  The reference's
