@@ -6,6 +6,7 @@
 // Scores are never materialised: K/V tiles are staged in shared memory, one thread owns one query
 // row (forward, dQ) or one key row (dK/dV) with its 32-wide vectors in registers.
 #include <math_constants.h>
+#include <cstdlib>
 #include "kernels.cuh"
 
 namespace bdetr {

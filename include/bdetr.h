@@ -398,7 +398,8 @@ int bdetr_heads_bwd(int M, int D, int Dh, int C, int A, const float *x, const bd
  * epilogue done, teardown).  Pass NULL to switch it off. */
 int bdetr_debug_set_timeline(long long *device_buf8);
 /* Debug / test aid: which tcgen05 attention-forward kernel the tensor-core mode uses.  0 = automatic (multi-stream
- * kernel for long sequences, one tile per CTA otherwise), 1 = always one tile per CTA, 2 = always multi-stream. */
+ * kernel for long sequences, one tile per CTA otherwise), 1 = always one tile per CTA, 2 = always multi-stream;
+ * 20 + n = multi-stream with n of every 8 exponential groups evaluated on the FMA pipe. */
 int bdetr_debug_force_attention_kernel(int which);
 
 /* Generic row-major GEMM used by the entry points above, exported for tests and benchmarks:

@@ -47,7 +47,7 @@ def test_matching_metric_and_loss_callables_vs_oracle():
     cost = dev(rng.random((B, T, Q)).astype(np.float32))
     mask, _ = MatchingMask()([cost, dev(n)])
     got = mm([dev(box), dev(pb)], assignment_mask=mask).cpu().numpy()
-    assert nerr(got, mask.cpu().numpy() * iou_ref) < 2e-6
+    assert nerr(got, mask.cpu().numpy() * iou_ref) < 1e-5        # (normalised by the few matched IoUs, not by the full matrix)
 
 
 def test_workspace_queries_cover_what_the_layers_allocate():
