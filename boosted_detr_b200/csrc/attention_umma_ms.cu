@@ -27,7 +27,7 @@ constexpr int MS_BM = 128;         // query rows per stream
 constexpr int MS_KT = 128;         // keys per tile
 constexpr int MS_HD = 32;
 constexpr int MS_STAGES = 3;
-constexpr int MS_THREADS = 64 + 128 * MS_NS;
+constexpr int MS_THREADS = 64 + 128 * MS_NS + 32 * (MS_NS - 1);      // TMA warp, 3 MMA issuer warps (1, 14, 15), 12 softmax warps
 constexpr uint32_t MS_TILE_BYTES = MS_KT * MS_HD * 4;     // 16 KB (Q, K and V tiles all have this size)
 constexpr uint32_t MS_TMEM_COLS = 512;
 constexpr uint32_t MS_STREAM_COLS = 160;
@@ -86,7 +86,7 @@ attention_fwd_umma_ms_kernel(const __grid_constant__ CUtensorMap map_q, const __
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < MS_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < MS_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], nact); }   // every live stream's issuer releases the stage
         for (int j = 0; j < MS_NS; ++j) { mbar_init(&s_full[j], 1); mbar_init(&p_full[j], 128); mbar_init(&o_full[j], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -115,51 +115,36 @@ attention_fwd_umma_ms_kernel(const __grid_constant__ CUtensorMap map_q, const __
             }
             __syncwarp();
         }
-    } else if (warp == 1) {
-        // MMA issuer: the whole warp walks the schedule (uniform descriptors), one elected lane issues
-        constexpr uint32_t idesc_s = make_idesc_tf32(MS_BM, MS_KT, 0, 0);      // both K-major
-        constexpr uint32_t idesc_o = make_idesc_tf32(MS_BM, MS_HD, 0, 1);      // A from TMEM, B (V) MN-major
-        auto issue_s = [&](int j, int stage) {                                  // call inside elect_one()
-            const uint32_t q_addr = smem_u32(smem_q + j * MS_TILE_BYTES), k_addr = smem_u32(smem_k + stage * MS_TILE_BYTES);
+    } else if (warp == 1 || warp >= 2 + 4 * MS_NS) {
+        // MMA issuers: ONE WARP PER STREAM (warp 1 -> stream 0, warps 14 / 15 -> streams 1 / 2).  Each walks its own
+        // stream's tiles with blocking barrier waits: wait P_j(t) -> O_j += P_j V(t) -> S_j(t+1) = Q_j K(t+1)^T.  A single
+        // issuer polling three streams put its polling period and the other streams' ~20 MMA issues (one elected lane,
+        // ~25 cycles each) into every stream's critical path: the softmax warps waited ~2 000 cycles per tile for the
+        // next S.  The tensor pipe still executes in issue order, so S_j(t+1) cannot overwrite P_j(t) before PV has read it.
+        const int j = warp == 1 ? 0 : warp - (2 + 4 * MS_NS) + 1;
+        if (j < nact) {
+            constexpr uint32_t idesc_s = make_idesc_tf32(MS_BM, MS_KT, 0, 0);      // both K-major
+            constexpr uint32_t idesc_o = make_idesc_tf32(MS_BM, MS_HD, 0, 1);      // A from TMEM, B (V) MN-major
+            const uint32_t sbase = tmem_base + j * MS_STREAM_COLS;
+            auto issue_s = [&](int stage) {                                         // call inside elect_one()
+                const uint32_t q_addr = smem_u32(smem_q + j * MS_TILE_BYTES), k_addr = smem_u32(smem_k + stage * MS_TILE_BYTES);
 #pragma unroll
-            for (int i = 0; i < MS_HD / 8; ++i)
-                umma_tf32(tmem_base + j * MS_STREAM_COLS, make_smem_desc(q_addr + i * 32, 16, 1024, 2),
-                          make_smem_desc(k_addr + i * 32, 16, 1024, 2), idesc_s, i != 0);
-            umma_commit(&s_full[j]);
-        };
-        mbar_wait(q_full, 0);
-        mbar_wait(&kv_full[0], 0);
-        tc_fence_after();
-        if (elect_one()) {
-            for (int j = 0; j < nact; ++j) issue_s(j, 0);
-        }
-        __syncwarp();
-        // Streams are served in whatever order their probabilities become ready (non-blocking barrier tests): a stream
-        // never idles behind another one's softmax, so the three softmax phases spread out instead of marching in step,
-        // and the MUFU always has a stream to work on while another one's MMAs execute.
-        int tj[MS_NS], done[MS_STAGES];
-#pragma unroll
-        for (int j = 0; j < MS_NS; ++j) tj[j] = 0;
-#pragma unroll
-        for (int s = 0; s < MS_STAGES; ++s) done[s] = 0;
-        int remaining = nact * ntiles;
-        uint32_t idle = 0;
-        while (remaining > 0) {
-            bool served = false;
-#pragma unroll
-            for (int j = 0; j < MS_NS; ++j) {
-                const int t = tj[j];
-                if (j >= nact || t >= ntiles) continue;
-                if (!mbar_test(&p_full[j], t & 1)) continue;
+                for (int i = 0; i < MS_HD / 8; ++i)
+                    umma_tf32(sbase, make_smem_desc(q_addr + i * 32, 16, 1024, 2), make_smem_desc(k_addr + i * 32, 16, 1024, 2), idesc_s, i != 0);
+                umma_commit(&s_full[j]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            if (elect_one()) issue_s(0);
+            __syncwarp();
+            for (int t = 0; t < ntiles; ++t) {
                 const bool more = t + 1 < ntiles;
-                if (more && !mbar_test(&kv_full[(t + 1) % MS_STAGES], ((t + 1) / MS_STAGES) & 1)) continue;   // next K tile not landed yet
+                if (more) mbar_wait(&kv_full[(t + 1) % MS_STAGES], ((t + 1) / MS_STAGES) & 1);      // next K tile landed (usually long ago)
+                mbar_wait(&p_full[j], t & 1);
                 tc_fence_after();
                 const int s = t % MS_STAGES;
                 const uint32_t v_addr = smem_u32(smem_v + s * MS_TILE_BYTES);
-                const uint32_t sbase = tmem_base + j * MS_STREAM_COLS;
-                int dn = 0;
-#pragma unroll
-                for (int q = 0; q < MS_STAGES; ++q) if (q == s) dn = ++done[q];
                 if (elect_one()) {
                     // O_j (+)= P_j V: accumulated in TMEM across tiles (the softmax rescales it in place on the rare
                     // occasions the reference maximum is raised)
@@ -167,23 +152,14 @@ attention_fwd_umma_ms_kernel(const __grid_constant__ CUtensorMap map_q, const __
                     for (int i = 0; i < MS_KT / 8; ++i)
                         umma_tf32_ts(sbase + MS_O_COL, sbase + i * 8, make_smem_desc(v_addr + i * 1024, 4096, 512, 1), idesc_o, (t | i) != 0);
                     umma_commit(&o_full[j]);
-                    // the next tile's scores of this stream go out right behind its PV (in-order tensor pipe: they cannot
-                    // overwrite P before the PV above has consumed it)
-                    if (more) issue_s(j, (t + 1) % MS_STAGES);
-                    if (dn == nact) umma_commit(&kv_empty[s]);        // last stream through this K/V tile releases the stage
+                    if (more) issue_s((t + 1) % MS_STAGES);
+                    umma_commit(&kv_empty[s]);                   // this stream is done with K/V tile t (count = live streams)
                 }
                 __syncwarp();
-#pragma unroll
-                for (int q = 0; q < MS_STAGES; ++q) if (q == s && dn == nact) done[q] = 0;
-                tj[j] = t + 1;
-                --remaining;
-                served = true;
             }
-            if (!served) { if (++idle > SPIN_LIMIT) __trap(); __nanosleep(32); } else idle = 0;
         }
-        if (dbg_on) { dbg[8] = dt[0]; dbg[9] = dt[1]; dbg[10] = dt[2]; dbg[11] = dt[3]; dbg[12] = ntiles; }
     } else {
-        const int j = (warp - 2) >> 2;                  // stream
+        const int j = (warp - 2) >> 2;                  // stream (softmax warps 2 .. 13)
         const int q = warp & 3;                         // TMEM lane quadrant this warp may access
         if (j < nact) {
             const int q0 = q_base + j * MS_BM;
