@@ -36,6 +36,9 @@ HeadSaved = _ptr_struct("HeadSaved", ["h", "hn", "bn_mean", "bn_rstd", "bn_acc",
 HeadScratch = _ptr_struct("HeadScratch", ["d_logits", "d_hn", "d_h"])
 HeadsSaved = _ptr_struct("HeadsSaved", ["h", "bn_mean", "bn_rstd", "w2f", "b2f", "bn_part", "act0", "act1", "act2"])
 HeadsScratch = _ptr_struct("HeadsScratch", ["d_logits", "hTd", "colsum_d", "bn_s", "d_h"])
+NeckParams = _ptr_struct("NeckParams", ["bn1_gamma", "bn1_beta", "bn1_moving_mean", "bn1_moving_var", "conv_w", "conv_b",
+                                         "bn2_gamma", "bn2_beta", "bn2_moving_mean", "bn2_moving_var"])
+NeckSaved = _ptr_struct("NeckSaved", ["t", "wf", "bf", "part", "stat1", "stat2"])
 PTR3 = c_void_p * 3
 INT3 = c_int * 3
 
@@ -97,6 +100,8 @@ PROTOTYPES = {
     "bdetr_ffn_block_scratch_bytes": (c_size_t, [I, I]),
     "bdetr_heads_saved_bytes": (c_size_t, [I, I, I, I]),
     "bdetr_heads_scratch_bytes": (c_size_t, [I, I, I, I]),
+    "bdetr_backbone_neck_fwd": (c_int, [I, I, I, P, POINTER(NeckParams), F, F, I, P, POINTER(NeckSaved), I, P]),
+    "bdetr_backbone_neck_bwd": (c_int, [I, I, I, P, POINTER(NeckParams), I, POINTER(NeckSaved), P, POINTER(NeckParams), P, P, P]),
     "bdetr_inverse_tokenize": (c_int, [I, I, I, I, P, P, P, P, P, P, F, P]),
     "bdetr_comm_unique_id": (c_int, [P]),
     "bdetr_comm_init": (c_int, [POINTER(c_void_p), I, I, P]),

@@ -37,7 +37,7 @@ class BoostedDETR:
     def __init__(self, num_object_preds, image_size, num_encoder_blocks, num_encoder_heads, encoder_dim,
                  num_decoder_blocks, num_decoder_heads, decoder_dim, num_panoptic_heads=1, panoptic_dim=32,
                  vocab_dict=None, classification_only=False, attribute_weight=1.0, name="DETR",
-                 feature_shape=None, seed=0, **kwargs):
+                 feature_shape=None, seed=0, backbone_neck=False, backbone_channels=1792, **kwargs):
         self.name = name
         self.use_intermediate_predictions = True
         self.num_object_preds = num_object_preds
@@ -59,6 +59,11 @@ class BoostedDETR:
             self.image_size[0] // BACKBONE_STRIDE, self.image_size[1] // BACKBONE_STRIDE)
 
         Layer._rng = np.random.default_rng(seed)
+        # with backbone_neck=True the model starts one step earlier, at the EfficientNet output
+        # inputs['backbone_features'] [B, rows, cols, backbone_channels] (reference boosted_model.py:195-196)
+        from .backbone import BackboneNeck
+        self.BackboneNeck = BackboneNeck(encoder_dim, name="BackboneNeck") if backbone_neck else None
+        self.backbone_channels = backbone_channels
         N = num_decoder_blocks
         self.EncoderTransformerBlocks = [ImageEncoderAttention(1, num_encoder_heads, name=f"ImageEncoderAttention_{i}")
                                          for i in range(N)]
@@ -89,7 +94,8 @@ class BoostedDETR:
 
     # -- structure -----------------------------------------------------------------------------
     def layers(self):
-        return [*self.EncoderTransformerBlocks, self.DecoderPrep, *self.DecoderBlocks, *self.CategoryBlocks,
+        neck = [self.BackboneNeck] if self.BackboneNeck is not None else []
+        return [*neck, *self.EncoderTransformerBlocks, self.DecoderPrep, *self.DecoderBlocks, *self.CategoryBlocks,
                 *self.AttributeBlocks, *self.BoxBlocks]
 
     def get_config(self):
@@ -104,7 +110,10 @@ class BoostedDETR:
     def build(self, batch_size=2):
         """Creates all weights by running one tiny inference call (Keras builds lazily the same way)."""
         R, Cc = self.feature_shape
-        self.call({"features": zeros(batch_size, R, Cc, self.encoder_dim)}, training=False)
+        if self.BackboneNeck is not None:
+            self.call({"backbone_features": zeros(batch_size, R, Cc, self.backbone_channels)}, training=False)
+        else:
+            self.call({"features": zeros(batch_size, R, Cc, self.encoder_dim)}, training=False)
         self._flatten()
         return self
 
@@ -232,7 +241,12 @@ class BoostedDETR:
 
     def _prepare(self, inputs, training):
         self.h2d_bytes = 0
-        feats = self._to_device("features", inputs["features"], "f32")
+        self._neck_ctx = None
+        if self.BackboneNeck is not None and "backbone_features" in inputs:
+            bf = self._to_device("backbone_features", inputs["backbone_features"], "f32")
+            feats, self._neck_ctx = self.BackboneNeck.forward([bf], training)
+        else:
+            feats = self._to_device("features", inputs["features"], "f32")
         y_true = None
         if training:
             y_true = [self._to_device("category", inputs["category"], "f32"),
@@ -501,6 +515,10 @@ class BoostedDETR:
         enc_tr, dec_tr, heads_tr, prep_tr = self._trainable_flags()
         # does anything trainable sit at or below encoder i (on the chain x_0 -> enc_0 -> enc_1 -> ...)?
         below = [any(enc_tr[:i + 1]) for i in range(N)]
+        neck_ctx = getattr(self, "_neck_ctx", None)
+        neck_tr = neck_ctx is not None and self.BackboneNeck.trainable
+        if neck_tr:
+            below = [True] * N                      # the neck sits below every encoder block
         # Gradient of the running prediction of block i = sum of the loss gradients of blocks i .. N-1 (every later block's
         # prediction contains it).  The N loss backward kernels only need forward quantities, so they all run at once,
         # each into its own slice of one zeroed buffer, and one suffix-sum kernel turns the slices into the running
@@ -583,15 +601,18 @@ class BoostedDETR:
             self._mark(f"bwd enc{i} may start (main)")
             enc = self.EncoderTransformerBlocks[i]
             d_out = d_encs[i]                # gradient of encoder i's output: decoder i's k/v paths (+ encoder i+1, accumulated)
-            if d_out is not None and (enc.trainable or (i > 0 and below[i - 1])):
+            if d_out is not None and (enc.trainable or (i > 0 and below[i - 1]) or (i == 0 and neck_tr)):
                 Bf, L, D = d_out.shape
                 R, Cc = self.feature_shape
-                need_dx = i > 0 and below[i - 1]
-                tgt = d_encs[i - 1] if need_dx else None
-                if need_dx:
+                need_dx = (i > 0 and below[i - 1]) or (i == 0 and neck_tr)
+                tgt = d_encs[i - 1] if (need_dx and i > 0) else None
+                if tgt is not None:
                     main.wait_event(evs[i - 1])                       # d_enc[i-1] must exist before it is accumulated into
-                enc.backward(ctx["blocks"][i]["enc"], d_out.view(Bf, R, Cc, D), d_x=None if tgt is None else tgt.view(Bf, R, Cc, D),
-                             acc=tgt is not None, need_dx=need_dx)
+                d_x0 = enc.backward(ctx["blocks"][i]["enc"], d_out.view(Bf, R, Cc, D), d_x=None if tgt is None else tgt.view(Bf, R, Cc, D),
+                                    acc=tgt is not None, need_dx=need_dx)
+                if i == 0 and neck_tr:
+                    self.BackboneNeck.backward(neck_ctx, d_x0)       # parameter gradients of the neck (the backbone is frozen)
+                    keep.append(d_x0)
             self._mark(f"bwd enc{i} done (main)")
             if self.grad_bucket_hook is not None and self._flat is not None:
                 _lib.call("bdetr_join", stream_ptr())                    # encoder i's parameter gradients
@@ -782,6 +803,8 @@ class BoostedDETR:
                 # all-reduced underneath the backward of blocks i-1 .. 0
                 _, lo, hi = self._buckets[N - 1 - i]
                 self.grad_bucket_hook(i, lo, hi, [self_ev])
+        if getattr(self, "_neck_ctx", None) is not None and self.BackboneNeck.trainable and d_x_next is not None:
+            self.BackboneNeck.backward(self._neck_ctx, d_x_next)
         main.wait_stream(dec_s)
         main.wait_stream(aux[2])
         self._mark("bwd joined (main)")

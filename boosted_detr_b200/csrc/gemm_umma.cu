@@ -208,6 +208,9 @@ gemm_umma_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ 
                 if (ep.act == 1) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+                } else if (ep.act == 2) {                          // tanh (BackboneNeck's 1x1 convolution, backbone.py:76-78)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
                 }
                 if (ep.relu_mask && row < ep.M) {
                     const float *mrow = ep.relu_mask + (size_t)row * ep.ldc + n0 + c0;

@@ -433,6 +433,30 @@ int bdetr_sgd_step(int n_chunks, const bdetr_opt_chunk *chunks,
                    float lr, const float *lr_dev, float momentum, int nesterov, float clipnorm, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * BackboneNeck (reference backbone.py:66-95): BatchNorm -> 1x1 Conv2D(Cin -> N, tanh) -> BatchNorm on
+ * the channels-last backbone feature map, M = B*rows*cols pixels.  One tcgen05 GEMM with BN1 folded into the weights,
+ * tanh in the epilogue, BN2 as one affine pass (round_out: stored tf32-rounded, ready to be block 0's operand).
+ * x_tc [M,Cin]: the backbone output rounded to tf32 (bdetr_round_tf32).  Keras BatchNormalization: momentum .99, eps 1e-3.
+ *   saved: t [M,N] tanh output, wf [Cin,N] / bf [N] folded weights, part scratch of max(ceil(M/128)*2*Cin, ceil(Cin/32)*N) floats,
+ *          stat1 [4,Cin] / stat2 [4,N] = mean, rstd, scale, shift of the two normalisations.
+ * Backward: parameter gradients only (the backbone is frozen in the reference, notebook cell 30); scratch d_u [M,N],
+ * gwf [Cin*N + N].
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    float *bn1_gamma, *bn1_beta, *bn1_moving_mean, *bn1_moving_var;   /* [Cin] */
+    float *conv_w, *conv_b;                                           /* [Cin,N] (the [1,1,Cin,N] Conv2D kernel), [N] */
+    float *bn2_gamma, *bn2_beta, *bn2_moving_mean, *bn2_moving_var;   /* [N] */
+} bdetr_neck_params;
+typedef struct {
+    float *t, *wf, *bf, *part, *stat1, *stat2;
+} bdetr_neck_saved;
+int bdetr_backbone_neck_fwd(int M, int Cin, int N, const float *x_tc, const bdetr_neck_params *w, float bn_eps, float bn_momentum,
+                            int training, float *out, const bdetr_neck_saved *saved, int round_out, void *stream);
+int bdetr_backbone_neck_bwd(int M, int Cin, int N, const float *x_tc, const bdetr_neck_params *w, int training,
+                            const bdetr_neck_saved *saved, const float *d_out, const bdetr_neck_params *gw, float *d_u, float *gwf,
+                            void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Inference tail: the numeric half of InverseTokenization.call (tokenizers.py:126-137) and the
  * confidence statistic of the early-exit path the reference lists as TODO (README.md:9).
  *   tokens_categories [B,Q] int32 = argmax_c cat_pred (first maximum, like tf.argmax)

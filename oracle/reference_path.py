@@ -120,6 +120,15 @@ def batch_norm(x, p, prefix, training, new_stats=None):
     return (x - mean) * torch.rsqrt(var + BN_EPS) * gamma + beta
 
 
+def backbone_neck(x4d, p, prefix="BackboneNeck", training=False, new_stats=None):
+    """BackboneNeck.call, backbone.py:90-95: batch_norm1 -> Conv2D(1x1, tanh) -> batch_norm2 on a channels-last map
+    (a 1x1 convolution is a Dense over the pixels; kernel [1,1,Cin,N])."""
+    x = batch_norm(x4d, p, prefix + "/batch_norm1", training, new_stats)
+    w = p[prefix + "/conv2d_downscaler/kernel"]
+    x = torch.tanh(x @ w.reshape(w.shape[-2], w.shape[-1]) + p[prefix + "/conv2d_downscaler/bias"])
+    return batch_norm(x, p, prefix + "/batch_norm2", training, new_stats)
+
+
 # ----------------------------------------------------------------------------------------
 # transformers.py
 # ----------------------------------------------------------------------------------------
@@ -417,6 +426,8 @@ def boosted_detr_call(p, features, targets, num_blocks, num_heads, training,
     drop = drop or Dropout(None)
     weights = weights or model_weights()
     x = features
+    if "BackboneNeck/conv2d_downscaler/kernel" in p and x.shape[-1] == p["BackboneNeck/conv2d_downscaler/kernel"].shape[-2]:
+        x = backbone_neck(x, p, "BackboneNeck", training, new_stats)      # boosted_model.py:195-196
     B, R, Cc, D = x.shape
     loss = cat_l = att_l = box_l = exist_l = 0.0
     iou = None
