@@ -473,6 +473,39 @@ def boosted_detr_call(p, features, targets, num_blocks, num_heads, training,
     return out
 
 
+def image_encoder_attention_n(x4d, p, prefix, num_blocks, num_heads, drop, training):
+    """ImageEncoderAttention.call with num_blocks encoder blocks (transformers.py:294-315); block j's dropout sites are 8j, 8j+1."""
+    B, R, Cc, D = x4d.shape
+    pos = p[prefix + "/positional_encoding"].reshape(1, R * Cc, D).expand(B, R * Cc, D)
+    x = x4d.reshape(B, R * Cc, D)
+    for j in range(num_blocks):
+        x = encoder_block(x, pos, p, f"{prefix}/EncoderBlock_{j}", num_heads, drop, j, training)
+    return x.reshape(B, R, Cc, D), pos.reshape(B, R, Cc, D)
+
+
+def detr_call(p, features, targets, num_encoder_blocks, num_decoder_blocks, num_heads, training, drop=None, weights=None,
+              new_stats=None, forced_mask=None):
+    """Plain DETR.call, /root/reference/ModelComponents/model.py:153-236, from the BackboneNeck output: one encoder
+    stack, a CHAIN of decoder blocks, one set of heads on the last decoder output, the matching loss at the last block."""
+    drop = drop or Dropout(None)
+    weights = weights or model_weights()
+    x = features
+    if "BackboneNeck/conv2d_downscaler/kernel" in p and x.shape[-1] == p["BackboneNeck/conv2d_downscaler/kernel"].shape[-2]:
+        x = backbone_neck(x, p, "BackboneNeck", training, new_stats)
+    x, pos = image_encoder_attention_n(x, p, "ImageEncoderAttention", num_encoder_blocks, num_heads, drop, training)
+    enc_value, dec, enc_key, _ = decoder_prep(x, pos, p)
+    for i in range(num_decoder_blocks):
+        dec = decoder_block(enc_value, dec, enc_key, p, f"DecoderBlock_{i}", num_heads, drop, i, training, self_attention=(i >= 1))
+    cat = category_head(dec, p, "CategoryPredictionHead", training, new_stats)
+    attr = attribute_head(dec, p, "AttributePredictionHead", training, new_stats)
+    box = box_head(dec, p, "BoxPredictionHead", training, new_stats)
+    out = {"preds": [cat, attr, box]}
+    if training:
+        losses, metrics, mask, cost = matching_loss(targets, [cat, attr, box], weights, mask=forced_mask)
+        out.update(loss=losses[0], losses=losses, iou=metrics, mask=mask, cost=cost)
+    return out
+
+
 def params_to_torch(params: dict, dtype=torch.float64, requires_grad=False) -> dict:
     out = {}
     for k, v in params.items():
