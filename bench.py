@@ -209,13 +209,26 @@ def roofline_blocks(cfg, B, flush, peaks):
     hpeak = peaks.get("hbm_gbs", 6650.0)
     src = "MEASURED_PEAKS.json (burst figures, kernel timed alone)" if peaks else "fallback 1590 TFLOP/s / 6650 GB/s (B200_PROFILING.md)"
     M = B * L
-    x = torch.randn(M, D, device="cuda"); wt = torch.randn(D, D, device="cuda"); bias = torch.randn(D, device="cuda")
-    y = torch.empty(M, D, device="cuda")
-    t_gemm = time_kernel(lambda: _lib.call("bdetr_gemm", M, D, D, ptr(x), 0, ptr(wt), 0, ptr(bias), 0, 0, ptr(y), stream_ptr()), flush=flush)
-    ach = 2.0 * M * D * D / t_gemm / 1e12
-    traffic, traffic_src = ncu_traffic("gemm_umma_kernel<128") if mode else (None, None)
-    main = {"bound": "tensor", "kernel": ("gemm_umma_kernel" if mode else "gemm_simt_kernel") + f" (Dense forward [{M},{D}]x[{D},{D}])",
+    import ctypes
+    x = torch.randn(M, D, device="cuda"); wt = [torch.randn(D, D, device="cuda") for _ in range(3)]
+    bias = [torch.randn(D, device="cuda") for _ in range(3)]
+    y = [torch.empty(M, D, device="cuda") for _ in range(3)]
+    if mode:
+        # the dominant GEMM of the fused path: the grouped q/k/v projection of one encoder block, [M,256] x 3 x [256,256]
+        # (bdetr_pos_projection is the same grouped tcgen05 launch: one shared input, three weight / bias / output groups)
+        Ws, bs, ys = _lib.PTR3(*[t.data_ptr() for t in wt]), _lib.PTR3(*[t.data_ptr() for t in bias]), _lib.PTR3(*[t.data_ptr() for t in y])
+        fn = lambda: _lib.call("bdetr_pos_projection", M, D, ptr(x), 3, ctypes.byref(Ws), ctypes.byref(bs), ctypes.byref(ys), stream_ptr())
+        flops, name = 2.0 * M * 3 * D * D, f"gemm_umma_kernel<128,...> grouped q/k/v projection [{M},{D}] x 3 x [{D},{D}]"
+        ncu_name = "gemm_umma_kernel<128, 3, 0, 1>"
+    else:
+        fn = lambda: _lib.call("bdetr_gemm", M, D, D, ptr(x), 0, ptr(wt[0]), 0, ptr(bias[0]), 0, 0, ptr(y[0]), stream_ptr())
+        flops, name, ncu_name = 2.0 * M * D * D, f"gemm_simt_kernel (Dense forward [{M},{D}]x[{D},{D}])", "gemm_simt_kernel"
+    t_gemm = time_kernel(fn, flush=flush)
+    ach = flops / t_gemm / 1e12
+    traffic, traffic_src = ncu_traffic(ncu_name) if mode else (None, None)
+    main = {"bound": "tensor", "kernel": name,
             "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes": 4.0 * (M * D + 3 * D * D + 3 * M * D) if mode else 4.0 * (2 * M * D + D * D),
             "peak_source": src, "us_per_launch": t_gemm * 1e6, "mode": "tf32" if mode else "fp32",
             "note": "peak is the measured bf16 cuBLAS figure; the TF32 tensor peak is half of it"}
     others = {}

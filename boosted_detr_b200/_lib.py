@@ -61,6 +61,7 @@ PROTOTYPES = {
     "bdetr_get_concurrency": (c_int, []),
     "bdetr_set_deferred_join": (c_int, [I]),
     "bdetr_join": (c_int, [P]),
+    "bdetr_join_into": (c_int, [P, P]),
     "bdetr_get_pdl": (c_int, []),
     "bdetr_launch_count": (c_longlong, []),
     "bdetr_reset_launch_count": (None, []),

@@ -615,12 +615,13 @@ class BoostedDETR:
                     keep.append(d_x0)
             self._mark(f"bwd enc{i} done (main)")
             if self.grad_bucket_hook is not None and self._flat is not None:
-                _lib.call("bdetr_join", stream_ptr())                    # encoder i's parameter gradients
                 _, lo, hi = self._buckets[N - 1 - i]
                 hook_evs = [self_evs[i], grad_evs[i]]
                 if i == 0:
                     hook_evs = [e for e in self_evs if e is not None] + [grad_evs[0]]
-                self.grad_bucket_hook(i, lo, hi, hook_evs)
+                # encoder i's parameter-gradient chains are joined INTO the consumer's stream (bucket pipeline), not into
+                # this one: the encoder chain keeps running
+                self.grad_bucket_hook(i, lo, hi, hook_evs, join_from=torch.cuda.current_stream())
         _lib.call("bdetr_join", stream_ptr())
         for bs in bstreams:
             main.wait_stream(bs)

@@ -105,7 +105,7 @@ int Branches::join_deferrable()
     return rc;
 }
 
-int join_pending(cudaStream_t main_stream)
+int join_pending(cudaStream_t main_stream, cudaStream_t waiter)
 {
     if (!concurrency_enabled()) return BDETR_OK;
     AuxPool *p = pool_for_current_device();
@@ -121,7 +121,7 @@ int join_pending(cudaStream_t main_stream)
     for (int i = 0; i < AUX_PER_GROUP; ++i) {
         if (!(mask & (1 << i))) continue;
         const int k = g * AUX_PER_GROUP + i;
-        if (cudaEventRecord(p->join_ev[k], p->st[k]) != cudaSuccess || cudaStreamWaitEvent(main_stream, p->join_ev[k], 0) != cudaSuccess) {
+        if (cudaEventRecord(p->join_ev[k], p->st[k]) != cudaSuccess || cudaStreamWaitEvent(waiter, p->join_ev[k], 0) != cudaSuccess) {
             set_error("bdetr_join: %s", cudaGetErrorString(cudaGetLastError()));
             return BDETR_E_CUDA;
         }
@@ -149,7 +149,8 @@ int Branches::join()
 extern "C" __attribute__((visibility("default"))) int bdetr_set_concurrency(int on) { bdetr::g_conc.store(on ? 1 : 0); return BDETR_OK; }
 extern "C" __attribute__((visibility("default"))) int bdetr_get_concurrency(void) { return bdetr::g_conc.load(); }
 extern "C" __attribute__((visibility("default"))) int bdetr_set_deferred_join(int on) { bdetr::g_defer.store(on ? 1 : 0); return BDETR_OK; }
-extern "C" __attribute__((visibility("default"))) int bdetr_join(void *stream) { return bdetr::join_pending(reinterpret_cast<cudaStream_t>(stream)); }
+extern "C" __attribute__((visibility("default"))) int bdetr_join(void *stream) { return bdetr::join_pending(reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<cudaStream_t>(stream)); }
+extern "C" __attribute__((visibility("default"))) int bdetr_join_into(void *stream, void *waiter) { return bdetr::join_pending(reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<cudaStream_t>(waiter)); }
 extern "C" __attribute__((visibility("default"))) int bdetr_version(void) { return 100; }
 extern "C" __attribute__((visibility("default"))) const char *bdetr_last_error(void) { return bdetr::g_err; }
 extern "C" __attribute__((visibility("default"))) int bdetr_set_mode(int mode)

@@ -26,7 +26,7 @@ struct Branches {
     bool on, shared;
 };
 bool concurrency_enabled();
-int join_pending(cudaStream_t main_stream);
+int join_pending(cudaStream_t main_stream, cudaStream_t waiter);
 
 // C[M,N] = (beta ? C : 0) + op(A)[M,K] @ op(B)[K,N] (+bias[n]) ; act 1 = relu ;
 // relu_mask != NULL: C[m,n] = 0 where relu_mask[m*ldc+n] <= 0 (backward of relu, applied last).

@@ -147,13 +147,17 @@ class DataParallel:
             self.comm_stream = torch.cuda.Stream()
         return self.comm_stream
 
-    def reduce_bucket(self, block: int, lo: int, hi: int, events=()):
+    def reduce_bucket(self, block: int, lo: int, hi: int, events=(), join_from=None):
         """All-reduce flat_grads[lo:hi] (boosted block `block`) on the communication stream, ordered after the
         caller's stream and `events`."""
         comm = self._comm()
         comm.wait_stream(torch.cuda.current_stream())
         for ev in events:
             comm.wait_event(ev)
+        if join_from is not None:          # deferred parameter-gradient chains forked from the caller's stream (bdetr_join_into)
+            import ctypes
+            from . import _lib
+            _lib.call("bdetr_join_into", ctypes.c_void_p(join_from.cuda_stream), ctypes.c_void_p(comm.cuda_stream))
         with torch.cuda.stream(comm):
             if self.world > 1:
                 allreduce_gradients(self.model._flat[1][lo:hi])

@@ -60,6 +60,9 @@ int bdetr_get_concurrency(void);
  * and everything the forward produces are always joined inside the call. */
 int bdetr_set_deferred_join(int on);
 int bdetr_join(void *stream);
+/* the same, but `waiter` (e.g. the communication stream that all-reduces the gradients) is ordered after the chains that
+ * were forked from `stream`, and `stream` itself keeps running */
+int bdetr_join_into(void *stream, void *waiter);
 int bdetr_get_pdl(void);
 /* Number of kernels launched by this library since the last reset (bench.py's gpu_launches). */
 long long bdetr_launch_count(void);

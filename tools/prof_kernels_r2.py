@@ -1,0 +1,56 @@
+"""Launches each round-2 hot kernel ONCE at BASELINE sizes after a warm-up (for `ncu --set full`; not a pytest file):
+grouped q/k/v projection, Dense+LayerNorm kernel, grouped wgrad / k-grouped dgrad (inside the fused encoder block),
+attention fwd / bwd at L = 400, the heads kernels, cost kernels at config 4 for both vocabularies, LSAP, matched loss."""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from util import synth_preds, synth_targets
+from boosted_detr_b200 import _lib
+from boosted_detr_b200.device import ptr, stream_ptr
+from boosted_detr_b200.layers import Layer
+from boosted_detr_b200.prediction_heads import (BoxPredictionHead, MultiClassPredictionHead, SingleClassPredictionHead,
+                                                heads_backward_fused, heads_forward_fused)
+from boosted_detr_b200.transformers import EncoderBlock
+
+lib = _lib.load(); lib.bdetr_set_mode(_lib.MODE_TF32)
+B, L, D, H, Q = 16, 400, 256, 8, 100
+Layer._rng = np.random.default_rng(0)
+x = torch.randn(B, L, D, device="cuda"); pos = torch.randn(L, D, device="cuda")
+enc = EncoderBlock(H, name="enc")
+heads = (SingleClassPredictionHead(82, D, Q, name="c"), MultiClassPredictionHead(3, D, Q, name="a"), BoxPredictionHead(D, Q, name="b"))
+dec = torch.randn(B, Q, D, device="cuda")
+rng = np.random.default_rng(0)
+sets = {}
+for (C, A) in ((82, 3), (48, 296)):
+    Bm, T, Qm = 256, 100, 300
+    tr = synth_targets(rng, Bm, T, C, A); pr = synth_preds(rng, Bm, Qm, C, A)
+    sets[(C, A)] = [torch.from_numpy(np.ascontiguousarray(v)).cuda() for v in (*tr, *pr)]
+cost = torch.empty(256, 100, 300, device="cuda")
+c4r = torch.empty(256, 100, dtype=torch.int32, device="cuda"); r4c = torch.empty(256, 300, dtype=torch.int32, device="cuda")
+st = torch.empty(256, dtype=torch.int32, device="cuda"); losses = torch.empty(5, 256, device="cuda"); iou = torch.empty(300, device="cuda")
+
+
+def once():
+    for blk in (enc.SelfAttentionBlock, enc.FeedForwardBlock):
+        blk.rate = 0.1
+    y, ctx = enc.forward([x, pos], training=True, dropout_keys=(11, 12))
+    d_pos = torch.zeros(L, D, device="cuda")
+    enc.backward(ctx, torch.randn_like(y), d_pos)
+    cums, hc = heads_forward_fused(heads, dec, True, None, 2.0)
+    heads_backward_fused(heads, hc, [torch.randn_like(c) for c in cums])
+    for (C, A), d in sets.items():
+        _lib.call("bdetr_cost_matrix_fwd", 256, 100, 300, C, A, ptr(d[0]), ptr(d[1]), ptr(d[2]), ptr(d[4]), ptr(d[5]), ptr(d[6]), 1000.0, 1.0, 1.0, ptr(cost), stream_ptr())
+    d = sets[(82, 3)]
+    _lib.call("bdetr_lsap_assign", 256, 100, 300, ptr(cost), ptr(d[3]), ptr(c4r), ptr(r4c), None, None, ptr(st), stream_ptr())
+    _lib.call("bdetr_matched_loss_fwd", 256, 100, 300, 82, 3, ptr(d[0]), ptr(d[1]), ptr(d[2]), ptr(d[3]), ptr(d[4]), ptr(d[5]), ptr(d[6]), ptr(c4r), ptr(r4c),
+              1000.0, 1.0, 1.0, 100.0, ptr(losses), ptr(iou), stream_ptr())
+    torch.cuda.synchronize()
+
+
+for _ in range(2):
+    once()
+torch.cuda.cudart().cudaProfilerStart()
+once()
+torch.cuda.cudart().cudaProfilerStop()
+print("ok")
