@@ -3,10 +3,10 @@
 //     out = LayerNorm_eps(z) * gamma + beta                                 (:149 / :191)
 // A [M,K] K-major activations, W a Keras kernel [K,256] (MN-major B operand), N = 256 = the model width, so one CTA owns
 // whole rows: 128 rows x 256 columns, fp32 accumulator in 256 TMEM columns, and the row statistics never leave the CTA.
-// Eight warps, all of them epilogue warps; warp 0 first runs the TMA producer loop and warp 1 (the TMEM allocator) the MMA
-// issue loop -- the epilogue cannot start before the last MMA anyway.  Epilogue phase 1: every thread moves the 128
-// accumulator columns of its TMEM lane (quarter warp & 3, column half warp / 4) into swizzled 32 x 32 boxes in the idle
-// pipeline stages.  Phase 2: one warp per row, lane = every 32nd column, exactly the access pattern of the stand-alone
+// 16 warps, all of them epilogue warps; warp 0 first runs the TMA producer loop and warp 1 (the TMEM allocator) the MMA
+// issue loop -- the epilogue cannot start before the last MMA anyway.  Epilogue phase 1: warp w moves two 32 x 32
+// accumulator blocks (TMEM lane quarter w & 3, column groups 2 (w / 4), + 1) into swizzled boxes in the idle pipeline stages.
+// Phase 2: one warp per row, lane = every 32nd column, exactly the access pattern of the stand-alone
 // LayerNorm kernel (coalesced 128-byte reads of the residual / positional rows, two-pass mean / centred variance by
 // warp shuffles, coalesced writes) -- but fed from shared memory: the GEMM result never goes to HBM.
 #include <cstring>
@@ -14,7 +14,9 @@
 
 namespace bdetr {
 
-constexpr int LN_BM = 128, LN_N = 256, LN_BK = 32, LN_STAGES = 4, LN_THREADS = 256;
+extern long long *g_umma_timeline;
+
+constexpr int LN_BM = 128, LN_N = 256, LN_BK = 32, LN_STAGES = 4, LN_THREADS = 512;
 constexpr uint32_t LN_A_STAGE = LN_BM * LN_BK * 4;      // 16 KB
 constexpr uint32_t LN_B_STAGE = LN_N * LN_BK * 4;       // 32 KB
 
@@ -26,6 +28,7 @@ struct LnEpilogue {
     float keep_scale; uint32_t thresh, key; const uint32_t *seed_dev;
     float *z, *out, *mean, *rstd;
     int write_z, round_out;
+    long long *dbg;       // optional clock64 stamps of CTA 0 (bdetr_debug_set_timeline)
 };
 
 __global__ void __launch_bounds__(LN_THREADS, 1)
@@ -45,6 +48,9 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnEp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * LN_BM;
     const int nkb = ep.num_kb;
+    const bool dbg_on = ep.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64;      // warp 2, lane 0
+#define LN_STAMP(slot) do { if (dbg_on) ep.dbg[slot] = clock64(); } while (0)
+    LN_STAMP(0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < LN_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -57,10 +63,14 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnEp
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_sync();
-    s_bias[threadIdx.x] = ep.bias ? ep.bias[threadIdx.x] : 0.0f;
-    s_gamma[threadIdx.x] = ep.gamma[threadIdx.x];
-    s_beta[threadIdx.x] = ep.beta[threadIdx.x];
+    LN_STAMP(1);
+    if (threadIdx.x < LN_N) {
+        s_bias[threadIdx.x] = ep.bias ? ep.bias[threadIdx.x] : 0.0f;
+        s_gamma[threadIdx.x] = ep.gamma[threadIdx.x];
+        s_beta[threadIdx.x] = ep.beta[threadIdx.x];
+    }
     __syncthreads();
+    LN_STAMP(2);
 
     if (warp == 0) {
         for (int i = 0; i < nkb; ++i) {
@@ -97,92 +107,129 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnEp
         }
     }
     {
-        // ---- epilogue phase 1: accumulator rows (one TMEM lane = one row per thread) -> shared memory, as 32 x 32 boxes
-        // with 128-byte swizzled rows inside the now idle pipeline stages (box (c, q) = columns 32c.., rows 32q..)
-        const int q = warp & 3, hf = warp >> 2;
+        // ---- epilogue phase 1: 32 warps, warp w moves the 32 x 32 accumulator block (TMEM lane quarter w & 3, column
+        // group w >> 2) into its swizzled box in the now idle pipeline stages (box (c, q) = columns 32c.., rows 32q..)
+        const int q = warp & 3, cg2 = warp >> 2;        // 16 warps: TMEM lane quarter x pair of 32-column groups
         mbar_wait(accum_full, 0);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + hf * 128;
+        LN_STAMP(3);
         uint32_t ra[32], rb[32];
-        tmem_ld32_issue(taddr, ra);
+        tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (2 * cg2) * 32, ra);
+        tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (2 * cg2 + 1) * 32, rb);
+        tmem_ld32_wait(ra);
+        tmem_ld32_wait(rb);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            uint32_t *cur = (c & 1) ? rb : ra, *nxt = (c & 1) ? ra : rb;
-            tmem_ld32_wait(cur);
-            if (c + 1 < 4) tmem_ld32_issue(taddr + (c + 1) * 32, nxt);
-            uint8_t *box = smem + (size_t)((hf * 4 + c) * 4 + q) * 4096;
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t *cur = h ? rb : ra;
+            uint8_t *box = smem + (size_t)((2 * cg2 + h) * 4 + q) * 4096;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<uint4 *>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(cur[4 * j], cur[4 * j + 1], cur[4 * j + 2], cur[4 * j + 3]);
         }
+        LN_STAMP(4);
     }
     __syncthreads();
+    LN_STAMP(5);
     {
-        // ---- epilogue phase 2: one warp per row (16 rows per warp), lane = column 32c + lane for c = 0..7: coalesced
-        // 128-byte reads of the residual / positional rows and 128-byte writes of z / out; row statistics by warp shuffles
+        // ---- epilogue phase 2: one warp per row (4 rows per warp, two at a time), lane = column 32c + lane for c = 0..7:
+        // coalesced 128-byte reads of the residual / positional rows and 128-byte writes of z / out, row statistics by
+        // warp shuffles.  A row is a pure latency chain (loads, two 5-step shuffle reductions, rsqrt): 32 resident warps
+        // per SM are what hides it -- with 8 warps this phase took 25 000 cycles, 2.5x the GEMM itself.
         uint32_t key = ep.key;
         if (ep.seed_dev) key = lowbias32(*ep.seed_dev ^ key);
-        float bias[8], gam[8], bet[8];
+        constexpr int RPW = LN_BM / (LN_THREADS / 32);  // rows per warp
+        // lane owns columns [4 lane, 4 lane + 4) and [128 + 4 lane, ...): every global / shared access is a 16-byte vector
+        // (a warp moves 512 contiguous bytes per instruction; with 4-byte accesses the 50-CTA kernel was bound by the
+        // per-SM load / store instruction rate: 51 B/clk)
+        const int col0 = 4 * lane;
+        const float4 b0 = *reinterpret_cast<const float4 *>(s_bias + col0), b1 = *reinterpret_cast<const float4 *>(s_bias + 128 + col0);
+        const float4 g0 = *reinterpret_cast<const float4 *>(s_gamma + col0), g1 = *reinterpret_cast<const float4 *>(s_gamma + 128 + col0);
+        const float4 t0 = *reinterpret_cast<const float4 *>(s_beta + col0), t1 = *reinterpret_cast<const float4 *>(s_beta + 128 + col0);
+        const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bet[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        constexpr int RI = 4;                           // rows in flight per warp: four independent latency chains interleaved
+#pragma unroll 1
+        for (int i = 0; i < RPW; i += RI) {
+            float v[RI][8];
+            float sum[RI], sq[RI], mean[RI];
+            bool live[RI];
+            float4 r0[RI], r1[RI];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { bias[c] = s_bias[c * 32 + lane]; gam[c] = s_gamma[c * 32 + lane]; bet[c] = s_beta[c * 32 + lane]; }
-        constexpr int RPW = LN_BM / 8;                  // rows per warp
-        float rs[2][8], ps[2][8];                       // residual / positional rows, double-buffered one row ahead
-        auto load_row = [&](int rloc, float *r8, float *p8) {
-            const int row = m0 + rloc;
-            if (row < ep.M) {
-                const float *rrow = ep.resid + (size_t)row * LN_N + lane;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) r8[c] = rrow[c * 32];
-                if (ep.pos) {
-                    const float *prow = ep.pos + (size_t)(row % ep.pos_period) * LN_N + lane;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) p8[c] = prow[c * 32];
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) p8[c] = 0.0f;
+            for (int u = 0; u < RI; ++u) {              // all global loads of the batch first
+                const int row = m0 + warp * RPW + i + u;
+                live[u] = row < ep.M;
+                r0[u] = r1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live[u]) {
+                    const size_t goff = (size_t)row * LN_N + col0;
+                    r0[u] = *reinterpret_cast<const float4 *>(ep.resid + goff); r1[u] = *reinterpret_cast<const float4 *>(ep.resid + goff + 128);
+                    if (ep.pos) {
+                        const float *prow = ep.pos + (size_t)(row % ep.pos_period) * LN_N + col0;
+                        const float4 p0 = *reinterpret_cast<const float4 *>(prow), p1 = *reinterpret_cast<const float4 *>(prow + 128);
+                        r0[u].x += p0.x; r0[u].y += p0.y; r0[u].z += p0.z; r0[u].w += p0.w;
+                        r1[u].x += p1.x; r1[u].y += p1.y; r1[u].z += p1.z; r1[u].w += p1.w;
+                    }
                 }
             }
-        };
-        load_row(warp * RPW, rs[0], ps[0]);
-#pragma unroll 2
-        for (int i = 0; i < RPW; ++i) {
-            const int rloc = warp * RPW + i, row = m0 + rloc;
-            if (i + 1 < RPW) load_row(rloc + 1, rs[(i + 1) & 1], ps[(i + 1) & 1]);
-            if (row >= ep.M) break;                     // rows are processed in order: the rest of this warp's rows are out of range too
-            const float *r8 = rs[i & 1], *p8 = ps[i & 1];
-            const int qq = rloc >> 5, rr = rloc & 31;
-            float v[8];
-            float sum = 0.0f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float acc = *reinterpret_cast<const float *>(smem + (size_t)(c * 4 + qq) * 4096 + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
-                float a = acc + bias[c];
-                if (ep.thresh) a = dropout_keep((uint32_t)((size_t)row * LN_N + c * 32 + lane), key, ep.thresh) ? a * ep.keep_scale : 0.0f;
-                v[c] = (r8[c] + p8[c]) + a;
-                sum += v[c];
+            for (int u = 0; u < RI; ++u) {
+                const int rloc = warp * RPW + i + u, row = m0 + rloc;
+                const int qq = rloc >> 5, rr = rloc & 31;
+                const uint8_t *sp = smem + (size_t)((lane >> 3) * 4 + qq) * 4096 + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4);
+                const float4 a0 = *reinterpret_cast<const float4 *>(sp), a1 = *reinterpret_cast<const float4 *>(sp + 16 * 4096);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float rv[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
+                sum[u] = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float a = av[c] + bias[c];
+                    const int col = (c < 4 ? col0 : 128 + col0) + (c & 3);
+                    if (ep.thresh) a = dropout_keep((uint32_t)((size_t)row * LN_N + col), key, ep.thresh) ? a * ep.keep_scale : 0.0f;
+                    v[u][c] = live[u] ? rv[c] + a : 0.0f;
+                    sum[u] += v[u][c];
+                }
             }
-            const float mean = warp_sum(sum) * (1.0f / LN_N);
-            float sq = 0.0f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) { const float d = v[c] - mean; sq = fmaf(d, d, sq); }
-            const float rstd = rsqrtf(warp_sum(sq) * (1.0f / LN_N) + ep.eps);
-            if (ep.write_z) {
-                float *zrow = ep.z + (size_t)row * LN_N + lane;
+            for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int c = 0; c < 8; ++c) zrow[c * 32] = v[c];
+                for (int u = 0; u < RI; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+#pragma unroll
+            for (int u = 0; u < RI; ++u) {
+                mean[u] = sum[u] * (1.0f / LN_N);
+                sq[u] = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { const float d = v[u][c] - mean[u]; sq[u] = fmaf(d, d, sq[u]); }
             }
-            float *orow = ep.out + (size_t)row * LN_N + lane;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float y = (v[c] - mean) * rstd * gam[c] + bet[c];
-                if (ep.round_out) y = tf32_rn(y);
-                orow[c * 32] = y;
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < RI; ++u) sq[u] += __shfl_xor_sync(0xffffffffu, sq[u], o);
+#pragma unroll
+            for (int u = 0; u < RI; ++u) {
+                if (!live[u]) continue;
+                const int row = m0 + warp * RPW + i + u;
+                const size_t goff = (size_t)row * LN_N + col0;
+                const float rstd = rsqrtf(sq[u] * (1.0f / LN_N) + ep.eps);
+                if (ep.write_z) {
+                    *reinterpret_cast<float4 *>(ep.z + goff) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+                    *reinterpret_cast<float4 *>(ep.z + goff + 128) = make_float4(v[u][4], v[u][5], v[u][6], v[u][7]);
+                }
+                float y[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    y[c] = (v[u][c] - mean[u]) * rstd * gam[c] + bet[c];
+                    if (ep.round_out) y[c] = tf32_rn(y[c]);
+                }
+                *reinterpret_cast<float4 *>(ep.out + goff) = make_float4(y[0], y[1], y[2], y[3]);
+                *reinterpret_cast<float4 *>(ep.out + goff + 128) = make_float4(y[4], y[5], y[6], y[7]);
+                if (lane == 0) { ep.mean[row] = mean[u]; ep.rstd[row] = rstd; }
             }
-            if (lane == 0) { ep.mean[row] = mean; ep.rstd[row] = rstd; }
         }
     }
+    LN_STAMP(6);
     tc_fence_before();
     __syncthreads();
+    LN_STAMP(7);
     if (warp == 1) tmem_dealloc(tmem_base, LN_N);
 }
 
@@ -203,7 +250,7 @@ int launch_gemm_ln(int M, int K, const float *A, const float *W, const float *bi
     ep.bias = bias; ep.resid = resid; ep.pos = pos; ep.pos_period = pos_period > 0 ? pos_period : 1;
     ep.gamma = gamma; ep.beta = beta; ep.eps = eps;
     ep.thresh = dropout_threshold(rate); ep.keep_scale = 1.0f / (1.0f - rate); ep.key = key; ep.seed_dev = seed_dev;
-    ep.z = z; ep.out = out; ep.mean = mean; ep.rstd = rstd; ep.write_z = z != nullptr; ep.round_out = round_out;
+    ep.dbg = g_umma_timeline; ep.z = z; ep.out = out; ep.mean = mean; ep.rstd = rstd; ep.write_z = z != nullptr; ep.round_out = round_out;
     const size_t smem = (size_t)LN_STAGES * (LN_A_STAGE + LN_B_STAGE) + (2 * LN_STAGES + 1) * 8 + 64 + (3 * LN_N + 512) * 4 + 1024;
     static bool optin = false;
     if (!optin) {
