@@ -111,4 +111,20 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // error picked up by BDETR_CHECK_LAUNCH
 }
 
+// the same for a kernel that runs as thread-block clusters of `cluster` CTAs along x
+template <typename... KArgs, typename... Args>
+static inline void launch_cluster_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, int cluster, size_t smem, cudaStream_t s, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace bdetr

@@ -16,5 +16,8 @@ for M in (6400, 1600):
     for rep in range(2):
         ffn.forward([x], training=True, dropout_key=5); torch.cuda.synchronize()
         t = buf.cpu().numpy(); d = t - t[0]
-        print(f"M{M}: pdl wait done {d[1]} | params staged {d[2]} | accumulator ready {d[3]} | phase 1 done {d[4]} | sync {d[5]} | phase 2 done {d[6]} | end {d[7]}")
+        if os.environ.get("BDETR_LN_SPLIT", "4") == "1":
+            print(f"M{M}: pdl wait done {d[1]} | params staged {d[2]} | accumulator ready {d[3]} | phase 1 done {d[4]} | sync {d[5]} | phase 2 done {d[6]} | end {d[7]}")
+        else:
+            print(f"M{M} split: pdl wait done {d[1]} | tile staged, loops done, mask hashed {d[2]} | accumulator ready {d[3]} | partials pushed {d[7]} | z store issued, cluster barrier passed {d[4]} | statistics merged {d[8]} | out boxes read by TMA {d[5]} | end {d[6]}")
     lib.bdetr_debug_set_timeline(None)
