@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libbdetr.so")
 BDETR_OK = 0
 BDETR_E_BAD_SHAPE, BDETR_E_CUDA, BDETR_E_INVALID_COST, BDETR_E_INFEASIBLE, BDETR_E_NULL, BDETR_E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 BDETR_E_NCCL = -7
-MODE_FP32, MODE_TF32 = 0, 1
+MODE_FP32, MODE_TF32, MODE_FP16 = 0, 1, 2
 
 
 class BdetrError(RuntimeError):
@@ -26,7 +26,7 @@ def _ptr_struct(name, fields):
 
 
 AttnParams = _ptr_struct("AttnParams", ["wq", "bq", "wk", "bk", "wv", "bv", "wo", "bo", "ln_gamma", "ln_beta"])
-AttnSaved = _ptr_struct("AttnSaved", ["qp", "kp", "vp", "o", "lse", "z", "mean", "rstd"])
+AttnSaved = _ptr_struct("AttnSaved", ["qp", "kp", "vp", "o", "lse", "z", "mean", "rstd", "ws16"])
 AttnScratch = _ptr_struct("AttnScratch", ["d_qp", "d_kp", "d_vp", "d_o", "d_z", "delta"])
 FfnParams = _ptr_struct("FfnParams", ["w1", "b1", "w2", "b2", "ln_gamma", "ln_beta"])
 FfnSaved = _ptr_struct("FfnSaved", ["h", "z", "mean", "rstd"])
@@ -56,6 +56,8 @@ PROTOTYPES = {
     "bdetr_last_error": (c_char_p, []),
     "bdetr_set_mode": (c_int, [I]),
     "bdetr_get_mode": (c_int, []),
+    "bdetr_attention_f16_workspace_bytes": (c_size_t, [I, I, I, I, I]),
+    "bdetr_attention_core_fwd_f16": (c_int, [I, I, I, I, I, P, P, P, P, P, P, P]),
     "bdetr_set_pdl": (c_int, [I]),
     "bdetr_set_concurrency": (c_int, [I]),
     "bdetr_get_concurrency": (c_int, []),
@@ -152,6 +154,11 @@ def load() -> ctypes.CDLL:
         lib.bdetr_set_concurrency(int(os.environ["BDETR_CONCURRENCY"]))
     _lib = lib
     return lib
+
+
+def tc_mode() -> bool:
+    """True in the tensor-core modes (BDETR_MODE_TF32, and BDETR_MODE_FP16 = the same with fp16 attention operands)."""
+    return load().bdetr_get_mode() in (MODE_TF32, MODE_FP16)
 
 
 def check(code: int) -> None:

@@ -158,7 +158,7 @@ class BoostedDETR:
             layer.invalidate()
 
     def tensor_core_mode(self):
-        return _lib.load().bdetr_get_mode() == _lib.MODE_TF32
+        return _lib.tc_mode()
 
     def refresh_shadow(self):
         """tensor-core mode: re-round the Dense kernels into their tf32 shadows (one pass over the flat buffer)."""

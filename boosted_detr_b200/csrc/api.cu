@@ -9,6 +9,7 @@ namespace bdetr {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_mode{BDETR_MODE_FP32};
+static std::atomic<int> g_attn_f16{0};       // BDETR_MODE_FP16 = tensor-core mode + fp16 attention operands
 static std::atomic<int> g_pdl{1};
 bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 
@@ -24,6 +25,7 @@ static thread_local int t_mode_override = -1;
 int current_mode() { return t_mode_override >= 0 ? t_mode_override : g_mode.load(std::memory_order_relaxed); }
 ModeScope::ModeScope(int mode) : saved(t_mode_override) { t_mode_override = mode; }
 ModeScope::~ModeScope() { t_mode_override = saved; }
+bool attention_f16_enabled() { return g_attn_f16.load(std::memory_order_relaxed) != 0; }
 
 // ---- auxiliary stream pool (per device) ---------------------------------------------------------------------
 static std::atomic<int> g_conc{1};
@@ -155,14 +157,16 @@ extern "C" __attribute__((visibility("default"))) int bdetr_version(void) { retu
 extern "C" __attribute__((visibility("default"))) const char *bdetr_last_error(void) { return bdetr::g_err; }
 extern "C" __attribute__((visibility("default"))) int bdetr_set_mode(int mode)
 {
-    if (mode != BDETR_MODE_FP32 && mode != BDETR_MODE_TF32) {
+    if (mode != BDETR_MODE_FP32 && mode != BDETR_MODE_TF32 && mode != BDETR_MODE_FP16) {
         bdetr::set_error("bdetr_set_mode: unknown mode %d", mode);
         return BDETR_E_UNSUPPORTED;
     }
-    bdetr::g_mode.store(mode);
+    // internally the fp16 mode IS the tensor-core mode (every `mode == TF32` dispatch holds) plus the operand switch
+    bdetr::g_mode.store(mode == BDETR_MODE_FP16 ? BDETR_MODE_TF32 : mode);
+    bdetr::g_attn_f16.store(mode == BDETR_MODE_FP16 ? 1 : 0);
     return BDETR_OK;
 }
-extern "C" __attribute__((visibility("default"))) int bdetr_get_mode(void) { return bdetr::g_mode.load(); }
+extern "C" __attribute__((visibility("default"))) int bdetr_get_mode(void) { return bdetr::g_attn_f16.load() ? BDETR_MODE_FP16 : bdetr::g_mode.load(); }
 extern "C" __attribute__((visibility("default"))) long long bdetr_launch_count(void) { return bdetr::g_launches.load(); }
 extern "C" __attribute__((visibility("default"))) void bdetr_reset_launch_count(void) { bdetr::g_launches.store(0); }
 extern "C" __attribute__((visibility("default"))) int bdetr_set_pdl(int on) { bdetr::g_pdl.store(on ? 1 : 0); return BDETR_OK; }

@@ -318,6 +318,20 @@ bool encode_tensor_map_2d(CUtensorMap *map, const float *base, long long rows, i
     return r == CUDA_SUCCESS;
 }
 
+bool encode_tensor_map_2d_f16(CUtensorMap *map, const void *base, long long rows, int cols, int ld, int box_cols, int box_rows)
+{
+    EncodeTiledFn cuTensorMapEncodeTiled = encode_tiled_fn();
+    if (!cuTensorMapEncodeTiled) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 constexpr bool UMMA_SHALLOW_DEFAULT = true;
 
 template <int BN, int STAGES>

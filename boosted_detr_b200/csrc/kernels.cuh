@@ -73,6 +73,11 @@ bool attention_umma_ms_eligible(int B, int H, int Lq, int Lk);
 int launch_attention_fwd_umma_ms(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
                                  float *o, float *lse, int round_out, cudaStream_t s);
 extern int g_force_attention_kernel;
+// fp16-operand variant (attention_umma_ms_f16.cu): q / k / v are cast into ws16 (attention_f16_workspace_bytes) first
+size_t attention_f16_workspace_bytes(int B, int H, int Lq, int Lk, int d);
+int launch_attention_fwd_umma_ms_f16(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
+                                     void *ws16, float *o, float *lse, int round_out, cudaStream_t s);
+bool attention_f16_enabled();
 // tcgen05 flash attention forward (attention_umma.cu)
 bool attention_umma_eligible(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp);
 int launch_attention_fwd_umma(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,

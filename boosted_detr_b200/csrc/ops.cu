@@ -69,6 +69,21 @@ API int bdetr_attention_core_fwd(int B, int H, int Lq, int Lk, int d, const floa
     return launch_attention_fwd(B, H, Lq, Lk, d, qp, kp, vp, o, lse, 0, as_stream(stream));
 }
 
+API size_t bdetr_attention_f16_workspace_bytes(int B, int H, int Lq, int Lk, int d)
+{
+    if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return 0;
+    return attention_f16_workspace_bytes(B, H, Lq, Lk, d);
+}
+
+API int bdetr_attention_core_fwd_f16(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
+                                     void *ws16, float *o, float *lse, void *stream)
+{
+    BDETR_REQUIRE(qp && kp && vp && o && lse && ws16, BDETR_E_NULL, "null pointer");
+    BDETR_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0, BDETR_E_BAD_SHAPE, "bad attention shape");
+    BDETR_REQUIRE(attention_f16_workspace_bytes(B, H, Lq, Lk, d) > 0, BDETR_E_UNSUPPORTED, "shape not served by the fp16 attention kernel");
+    return launch_attention_fwd_umma_ms_f16(B, H, Lq, Lk, d, qp, kp, vp, ws16, o, lse, 0, as_stream(stream));
+}
+
 API int bdetr_attention_block_bwd(int B, int Lq, int Lk, int D, int H,
                                   const float *query, const float *key, const float *value,
                                   const bdetr_attn_params *w, float dropout_rate, uint32_t dropout_key,

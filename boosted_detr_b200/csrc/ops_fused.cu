@@ -97,7 +97,10 @@ API int bdetr_attention_fused_fwd(int B, int Lq, int Lk, int D, int H, const flo
         TRY(proj_group_fwd(Mk, D, memory, 2, pkv, tkv, Lk, s));
         TRY(br.join());
     }
-    TRY(launch_attention_fwd(B, H, Lq, Lk, D / H, sv->qp, sv->kp, sv->vp, sv->o, sv->lse, 1, s));
+    if (attention_f16_enabled() && sv->ws16 && attention_f16_workspace_bytes(B, H, Lq, Lk, D / H) > 0)
+        TRY(launch_attention_fwd_umma_ms_f16(B, H, Lq, Lk, D / H, sv->qp, sv->kp, sv->vp, sv->ws16, sv->o, sv->lse, 1, s));
+    else
+        TRY(launch_attention_fwd(B, H, Lq, Lk, D / H, sv->qp, sv->kp, sv->vp, sv->o, sv->lse, 1, s));
     // sv->o is [B,H,Lq,d], read back as [B*Lq, D] with no permute (reference transformers.py:100, quirk Q1)
     TRY(launch_gemm_ln(Mq, D, sv->o, w->wo, w->bo, query, rpos, Lq, w->ln_gamma, w->ln_beta, ln_eps, dropout_rate, dropout_key,
                        dropout_seed_dev, training ? sv->z : nullptr, out, sv->mean, sv->rstd, 1, s));

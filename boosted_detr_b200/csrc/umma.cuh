@@ -275,6 +275,55 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// ---- fp16-operand forms (kind::f16: A / B fp16, fp32 accumulator; UMMA_K = 16) ----------------------------------
+// Instruction descriptor: c_format F32 = 1 [4,6), a/b format F16 = 0 [7,10)/[10,13), majors [15]/[16], N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn, int b_mn)
+{
+    return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// A operand (fp16 pairs packed two per 32-bit column, even k in the low half) from tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16_u(uint32_t taddr, const uint32_t v[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+// {lo, hi} -> packed fp16 pair (round to nearest), lo in the low half
+__device__ __forceinline__ uint32_t pack_f16x2_rn(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t mul_f16x2(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+// host: 2D fp16 tensor map over a row-major [rows, cols] matrix of halves (ld in elements), 64-byte boxes rows (32 halves):
+// SWIZZLE_64B, the layout of K-major and MN-major kind::f16 operands with 32 elements along the contiguous dimension
+bool encode_tensor_map_2d_f16(CUtensorMap *map, const void *base, long long rows, int cols, int ld, int box_cols, int box_rows);
+
 // host: 2D fp32 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements).
 // mn_major selects the 32B-atom swizzle that MN-major 32-bit UMMA operands require.
 bool encode_tensor_map_2d(CUtensorMap *map, const float *base, long long rows, int cols, int ld, int box_cols, int box_rows,

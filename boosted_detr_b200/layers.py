@@ -109,7 +109,7 @@ class Layer:
     def gemm_weights(self):
         """Weights as the GEMMs should read them: tf32-rounded shadows of the Dense kernels in tensor-core mode."""
         from . import _lib
-        if self._shadow and _lib.load().bdetr_get_mode() == _lib.MODE_TF32:
+        if self._shadow and _lib.tc_mode():
             return {**self._weights, **self._shadow}, 1
         return self._weights, 0
 

@@ -58,7 +58,7 @@ class MultiheadAttention(Layer):
         Lk, H, d = key.shape[1], self.num_attention_heads, self.dim
         P = H * d
         w, _ = self.gemm_weights()
-        rnd = 1 if _lib.load().bdetr_get_mode() == _lib.MODE_TF32 else 0
+        rnd = 1 if _lib.tc_mode() else 0
 
         def dense(x, nm, rows, n_in, n_out):
             y = empty(rows, n_out)
@@ -166,7 +166,7 @@ class AttentionBlock(Layer):
 
 def fused_path(D=256):
     """The fused tensor-core entry points (include/bdetr.h) serve tensor-core mode at the model width 256."""
-    return D == 256 and _lib.load().bdetr_get_mode() == _lib.MODE_TF32
+    return D == 256 and _lib.tc_mode()
 
 
 def make_fold(pos=None, tab_q=None, tab_k=None, resid_pos=False, pos_tc=None):
@@ -208,6 +208,11 @@ def _attn_forward_fused(self, query, memory, fold, training=False, dropout_key=0
     out = empty(B, Lq, D)
     rate = self.rate if training else 0.0
     w, _ = self._structs()
+    lib = _lib.load()
+    if lib.bdetr_get_mode() == _lib.MODE_FP16:          # fp16 copies of q / k / v for the long-sequence attention kernel
+        n16 = lib.bdetr_attention_f16_workspace_bytes(B, H, Lq, Lk, D // H)
+        if n16:
+            sv["ws16"] = torch.empty(n16 // 2, dtype=torch.float16, device=query.device)
     svs = _struct(_lib.AttnSaved, sv)
     _lib.call("bdetr_attention_fused_fwd", B, Lq, Lk, D, H, ptr(query), ptr(memory), ctypes.byref(fold) if fold is not None else None,
               ctypes.byref(w), rate, dropout_key, ptr(seed_dev), LN_EPS, 1 if training else 0, ptr(out), ctypes.byref(svs), stream_ptr())
@@ -451,7 +456,7 @@ class ImageEncoderAttention(Layer):
         """[L,D] positional table as a tensor-core operand: its tf32-rounded shadow when the model keeps one."""
         pos = self._weights["positional_encoding"]
         sh = self._shadow.get("positional_encoding")
-        t = sh if (sh is not None and _lib.load().bdetr_get_mode() == _lib.MODE_TF32) else pos
+        t = sh if (sh is not None and _lib.tc_mode()) else pos
         return t.view(-1, pos.shape[-1])
 
     def forward(self, inputs, training=False, dropout_keys=None, seed_dev=None, tabs=None):

@@ -38,6 +38,11 @@ typedef enum {
 /* compute modes for the dense (GEMM / attention) kernels */
 #define BDETR_MODE_FP32 0 /* fp32 SIMT FFMA everywhere: the 1e-5 parity mode                   */
 #define BDETR_MODE_TF32 1 /* TF32 operands (10-bit mantissa) via TMA, fp32 accumulate in TMEM on tcgen05 (1e-3 mode) */
+#define BDETR_MODE_FP16 2 /* BDETR_MODE_TF32 with fp16 attention operands where the fp16 kernel serves the shape (long
+                           * sequences: the config-5 encoder self-attention): q / k / v and the softmax weights P are fp16
+                           * (tcgen05.mma kind::f16), accumulation fp32 -- the reference's Keras `mixed_float16` policy
+                           * (parameters.py:73).  Needs bdetr_attn_saved.ws16 / the *_f16 entry point's workspace; shapes the
+                           * fp16 kernel does not serve, and every backward, run exactly as in BDETR_MODE_TF32. */
 
 int bdetr_version(void);
 const char *bdetr_last_error(void);
@@ -171,6 +176,8 @@ typedef struct {
     float *lse;          /* [B,H,Lq] log-sum-exp of the scaled scores                        */
     float *z;            /* [B,Lq,D] pre-LayerNorm sum                                       */
     float *mean, *rstd;  /* [B*Lq] LayerNorm statistics                                      */
+    void *ws16;          /* BDETR_MODE_FP16 only (else NULL): bdetr_attention_f16_workspace_bytes() bytes, 128-byte
+                          * aligned, for the fp16 copies of qp / kp / vp; NULL keeps the TF32 kernel        */
 } bdetr_attn_saved;
 
 /* backward scratch: d_qp [B,Lq,D], d_kp, d_vp [B,Lk,D], d_o [B,H,Lq,d], d_z [B,Lq,D], delta [B,H,Lq] */
@@ -197,6 +204,14 @@ int bdetr_attention_block_fwd(int B, int Lq, int Lk, int D, int H,
  * Tensor-core mode runs the tcgen05/TMEM flash kernel; fp32 mode the SIMT kernel. */
 int bdetr_attention_core_fwd(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
                              float *o, float *lse, void *stream);
+
+/* fp16-operand attention core (BDETR_MODE_FP16; reference policy: parameters.py:73 `mixed_float16`).  Same contract as
+ * bdetr_attention_core_fwd; ws16 = bdetr_attention_f16_workspace_bytes(...) bytes of caller-owned scratch (fp16 copies of
+ * qp / kp / vp).  The workspace query returns 0 for shapes the fp16 kernel does not serve (it needs head dim 32, Lq >= 1536,
+ * Lk >= 1024 and at least 148 CTAs of 384 query rows); the entry point then returns BDETR_E_UNSUPPORTED. */
+size_t bdetr_attention_f16_workspace_bytes(int B, int H, int Lq, int Lk, int d);
+int bdetr_attention_core_fwd_f16(int B, int H, int Lq, int Lk, int d, const float *qp, const float *kp, const float *vp,
+                                 void *ws16, float *o, float *lse, void *stream);
 
 /* Backward of the above.  Parameter gradients are ACCUMULATED into *gw.  d_query/d_key/d_value
  * may be NULL (not needed); acc_flags bit0/1/2 = accumulate into d_query/d_key/d_value instead of
