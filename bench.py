@@ -244,8 +244,20 @@ def roofline_blocks(cfg, B, flush, peaks):
     others["attention_core_fwd_L400"] = attn(B, L, 50)
     if mode:
         others["attention_core_fwd_L20020_config5"] = attn(2, 20020, 2)
-        tr_, src_ = ncu_traffic("attention_fwd_umma_ms")
+        tr_, src_ = ncu_traffic("attention_fwd_umma_ms_kernel")
         others["attention_core_fwd_L20020_config5"].update(traffic=tr_, traffic_source=src_)
+        # the fp16-operand kernel of BDETR_MODE_FP16 (cast of q / k / v included in the timed launch pair)
+        q, k, v = (torch.randn(2, 20020, D, device="cuda") for _ in range(3))
+        o, lse = torch.empty(2, H, 20020, D // H, device="cuda"), torch.empty(2, H, 20020, device="cuda")
+        ws = torch.empty(_lib.load().bdetr_attention_f16_workspace_bytes(2, H, 20020, 20020, D // H) // 2, dtype=torch.float16, device="cuda")
+        t16 = time_kernel(lambda: _lib.call("bdetr_attention_core_fwd_f16", 2, H, 20020, 20020, D // H, ptr(q), ptr(k), ptr(v), ptr(ws), ptr(o),
+                                            ptr(lse), stream_ptr()), reps=2, iters=5, flush=flush)
+        a16 = 4.0 * 2 * 20020 * 20020 * D / t16 / 1e12
+        tr_, src_ = ncu_traffic("attention_fwd_umma_ms_f16")
+        others["attention_core_fwd_L20020_config5_fp16"] = {"bound": "tensor", "achieved": a16, "peak": tpeak, "unit": "TFLOP/s", "frac": a16 / tpeak,
+                                                            "us_per_launch": t16 * 1e6, "shape": [2, H, 20020, 20020], "traffic": tr_,
+                                                            "traffic_source": src_, "note": "cast_f16x3_kernel + attention_fwd_umma_ms_f16_kernel"}
+        del q, k, v, o, lse, ws
     for name, (C, A) in (("cost_matrix_config4_C82_A3", (82, 3)), ("cost_matrix_config4_C48_A296", (48, 296))):
         rng = np.random.default_rng(0)
         Bm, T, Q = 256, 100, 300
@@ -592,6 +604,22 @@ def run_infer(cx, cfg, also_faithful=True):
              "tokens": c["rows"] * c["cols"], "algorithmic_tflops": flops / sec / 1e12, "launches_per_step": launches,
              "e2e": {"value": B * cx.world / e2e_sec, "unit": "images/s", "h2d_bytes_per_step": feats_h.numel() * 4,
                      "d2h_bytes_per_step": sum(h.numel() * 4 for h in hp), "ms_per_step": e2e_sec * 1e3}}
+        if not tag and lib.bdetr_get_mode() == _lib.MODE_TF32:
+            # the same forward with fp16 attention operands (BDETR_MODE_FP16 = the reference's mixed_float16 policy)
+            lib.bdetr_set_mode(_lib.MODE_FP16)
+            try:
+                for _ in range(2):
+                    fn()
+                p16 = fn()
+                torch.cuda.synchronize()
+                sec16 = cx.timed_device(fn, steps)
+                e2e16, _ = cx.timed_e2e(e2e, steps)
+                dev = max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) for a, b in zip(p16, preds))
+                r["fp16_operands"] = {"value": B * cx.world / sec16, "ms_per_step": sec16 * 1e3, "algorithmic_tflops": flops / sec16 / 1e12,
+                                      "e2e": {"value": B * cx.world / e2e16, "unit": "images/s", "ms_per_step": e2e16 * 1e3},
+                                      "max_normalised_prediction_difference_vs_tf32": dev}
+            finally:
+                lib.bdetr_set_mode(_lib.MODE_TF32)
         if tag:
             out[tag] = r
         else:
@@ -609,7 +637,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--no-extras", action="store_true", help="config 2 only: skip the compact configs 3 / 4 / 5 blocks")
-    ap.add_argument("--mode", default=os.environ.get("BDETR_MODE", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--mode", default=os.environ.get("BDETR_MODE", "tf32"), choices=["fp32", "tf32", "fp16"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after the backward instead of per-block buckets under it")
     ap.add_argument("--no-conc", action="store_true", help="disable multi-stream concurrency inside the step (A/B timing)")
@@ -646,7 +674,7 @@ def main():
     rank, world, local = init_from_env()
     torch.cuda.set_device(local)
     lib = _lib.load()
-    lib.bdetr_set_mode(_lib.MODE_TF32 if args.mode == "tf32" else _lib.MODE_FP32)
+    lib.bdetr_set_mode({"tf32": _lib.MODE_TF32, "fp16": _lib.MODE_FP16, "fp32": _lib.MODE_FP32}[args.mode])
     lib.bdetr_set_pdl(0 if args.no_pdl else 1)
     lib.bdetr_set_concurrency(0 if args.no_conc else 1)
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
@@ -671,12 +699,12 @@ def main():
         sampler.join(timeout=2)
         line = {"metric": METRIC, "value": main_res["value"], "unit": "images/s", "n_gpus": world, "steps": main_res.get("steps", args.steps),
                 "warmup": max(args.warmup, 3), "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": cfg["scaling"],
-                "vs_baseline": None, "dtype": "tf32" if args.mode == "tf32" else "fp32", "data": "synthetic (random-init weights)",
+                "vs_baseline": None, "dtype": args.mode, "data": "synthetic (random-init weights)",
                 "config": config, "clocks": sampler.summary(), "e2e": main_res["e2e"],
                 "cuda_graph": not args.no_graph, "pdl": not args.no_pdl, "concurrent_streams": not args.no_conc,
                 "allreduce": ("none" if world == 1 or cfg["kind"] != "train" else "one call after backward" if args.no_overlap else
                               "per-block buckets overlapped with backward, inside the CUDA graph")}
-        for k in ("loss", "step_algorithmic_tflops", "matcher_us_per_image", "parts", "tokens", "algorithmic_tflops", "stride32_1050_tokens", "parameters"):
+        for k in ("loss", "step_algorithmic_tflops", "matcher_us_per_image", "parts", "tokens", "algorithmic_tflops", "stride32_1050_tokens", "parameters", "fp16_operands"):
             if k in main_res:
                 line[k] = main_res[k]
         state["line"] = line

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from test_dense_gpu import nerr
+from test_dense_gpu import _model_and_data, nerr
 
 pytestmark = pytest.mark.gpu
 
@@ -98,3 +98,40 @@ def test_f16_entry_refuses_unserved_shapes():
     assert lib.bdetr_attention_f16_workspace_bytes(16, 8, 400, 400, 32) == 0      # config 2: short sequences keep the TF32 kernels
     assert lib.bdetr_attention_f16_workspace_bytes(4, 8, 20020, 20020, 32) == 2 * 3 * 4 * 20020 * 256
     assert lib.bdetr_attention_f16_workspace_bytes(4, 8, 20020, 20020, 64) == 0
+
+
+def test_model_inference_fp16_mode_vs_fp64_oracle():
+    """BoostedDETR.call(training=False) in BDETR_MODE_FP16 at a sequence length the fp16 kernel serves without forcing
+    (4 images x 48 x 40 = 1 920 encoder tokens, 160 CTAs), two boosted blocks, against the fp64 oracle: predictions within
+    north_star's reduced-precision bar (1e-3 normalised max error), and the fp16 kernel must really have run
+    (the launch counter differs from TF32 mode by the cast kernel of each encoder block)."""
+    from oracle import reference_path as R
+    from boosted_detr_b200 import _lib
+    lib = _lib.load()
+    N, B, rows, cols = 2, 4, 48, 40
+    assert lib.bdetr_attention_f16_workspace_bytes(B, 8, rows * cols, rows * cols, 32) > 0
+    model, w, inputs = _model_and_data(N=N, B=B, rows=rows, cols=cols)
+    got, launches = {}, {}
+    try:
+        for name, mode in (("tf32", _lib.MODE_TF32), ("fp16", _lib.MODE_FP16)):
+            lib.bdetr_set_mode(mode)
+            assert lib.bdetr_get_mode() == mode
+            model.call({"features": inputs["features"]}, training=False)
+            lib.bdetr_reset_launch_count()
+            got[name] = [t.cpu().numpy() for t in model.call({"features": inputs["features"]}, training=False)]
+            torch.cuda.synchronize()
+            launches[name] = int(lib.bdetr_launch_count())
+    finally:
+        lib.bdetr_set_mode(_lib.MODE_FP32)
+    assert launches["fp16"] == launches["tf32"] + N, launches      # one cast launch per encoder self-attention
+    saved = R.ATTENTION_QUERY_CHUNK
+    R.ATTENTION_QUERY_CHUNK = 256
+    try:
+        out = R.boosted_detr_call(R.params_to_torch(w), torch.tensor(inputs["features"], dtype=torch.float64), None, N, 8, training=False)
+    finally:
+        R.ATTENTION_QUERY_CHUNK = saved
+    for i, nm in enumerate(["cat", "attr", "box"]):
+        ref = out["preds"][i].numpy()
+        e16, e32 = nerr(got["fp16"][i], ref), nerr(got["tf32"][i], ref)
+        print(f"inference {nm}: fp16 mode {e16:.2e}, tf32 mode {e32:.2e}")
+        assert e16 < 1e-3, nm
