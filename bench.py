@@ -733,6 +733,22 @@ def main():
             except Exception as e:                                # a secondary block must not lose the headline
                 others[str(oid)] = {"error": f"{type(e).__name__}: {e}"[:300]}
             torch.cuda.empty_cache()
+        # the other precision class north_star names: the same training step in the fp32 (1e-5 parity, SIMT) mode
+        if args.mode != "fp32" and time.time() - t_start < args.max_seconds * 0.7:
+            saved_steps = args.steps
+            try:
+                lib.bdetr_set_mode(_lib.MODE_FP32)
+                args.steps = min(args.steps, 10)
+                r, m32, _ = run_train(cx, 2, CONFIGS[2])
+                del m32
+                others["2_fp32_mode"] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "e2e": r["e2e"], "loss": r["loss"], "dtype": "fp32",
+                                         "steps": args.steps, "workload": describe(2, CONFIGS[2], per_gpu_batch(CONFIGS[2], world), world)}
+            except Exception as e:
+                others["2_fp32_mode"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            finally:
+                args.steps = saved_steps
+                lib.bdetr_set_mode({"tf32": _lib.MODE_TF32, "fp16": _lib.MODE_FP16, "fp32": _lib.MODE_FP32}[args.mode])
+            torch.cuda.empty_cache()
     if rank != 0:
         return                                                   # (no collective below this line: the other ranks are gone)
 
