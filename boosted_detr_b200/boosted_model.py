@@ -206,6 +206,15 @@ class BoostedDETR:
         Each (name, shape) has TWO staging slots used alternately, and a slot is only rewritten after the event recorded
         behind its previous H2D copy has completed -- the host may run ahead of the device (no sync in the step), and a
         single slot could be overwritten with batch k+1 while the copy of batch k was still queued."""
+        tdt = torch.int32 if dtype == "i32" else torch.float32
+        if isinstance(x, torch.Tensor) and x.is_pinned() and x.dtype == tdt and x.is_contiguous():
+            # caller-owned pinned memory: copied straight from it (no staging memcpy -- 82 MB per step at config 5); as
+            # with any non_blocking copy the caller must not rewrite the buffer before the step's stream has passed it
+            self.h2d_bytes += x.numel() * x.element_size()
+            if dst is None:
+                return x.to(require_cuda(), non_blocking=True)
+            dst.copy_(x.reshape(dst.shape), non_blocking=True)
+            return dst
         arr = x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
         arr = np.ascontiguousarray(arr, dtype=np.int32 if dtype == "i32" else np.float32)
         stage = getattr(self, "_staging", None)
@@ -213,7 +222,6 @@ class BoostedDETR:
             stage = self._staging = {}
         key = (name, arr.shape)
         if key not in stage:
-            tdt = torch.int32 if dtype == "i32" else torch.float32
             stage[key] = {"buf": [torch.empty(arr.shape, dtype=tdt).pin_memory() for _ in range(2)],
                           "ev": [None, None], "next": 0}
         st = stage[key]

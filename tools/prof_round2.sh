@@ -17,7 +17,11 @@ ncu --set full --clock-control none --import-source on --profile-from-start off 
 python tools/summarise_ncu.py gpurun_out/${TAG}_kernels.ncu-rep > gpurun_out/${TAG}_ncu_full_kernels.csv
 rm -f gpurun_out/${TAG}_kernels.ncu-rep      # (60 MB with sources: gpurun copies at most 64 MiB back; the csv summary is what profiles/ keeps)
 python tools/prof_attention.py > gpurun_out/${TAG}_attn_plain.log 2>&1 || { echo "prof_attention failed"; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:attention_fwd_umma_ms --launch-skip 2 --launch-count 1 \
+ncu --set full --clock-control none --import-source on -k regex:attention_fwd_umma_ms_kernel --launch-skip 2 --launch-count 1 \
     -o gpurun_out/${TAG}_attn_ms -f python tools/prof_attention.py > gpurun_out/${TAG}_attn_ncu.log 2>&1
 python tools/summarise_ncu.py gpurun_out/${TAG}_attn_ms.ncu-rep > gpurun_out/${TAG}_ncu_full_attention_ms.csv
+python tools/prof_attention.py f16 > gpurun_out/${TAG}_attn_f16_plain.log 2>&1 || { echo "prof_attention f16 failed"; exit 1; }
+ncu --set full --clock-control none --import-source on -k regex:attention_fwd_umma_ms_f16 --launch-skip 2 --launch-count 1 \
+    -o gpurun_out/${TAG}_attn_ms_f16 -f python tools/prof_attention.py f16 > gpurun_out/${TAG}_attn_f16_ncu.log 2>&1
+python tools/summarise_ncu.py gpurun_out/${TAG}_attn_ms_f16.ncu-rep > gpurun_out/${TAG}_ncu_full_attention_ms_f16.csv
 ls -la gpurun_out/${TAG}_*
