@@ -227,13 +227,19 @@ API int bdetr_ffn_fused_bwd(int M, int D, const float *x, const bdetr_ffn_params
     TRY(launch_res_ln_bwd(M, D, d_out, sv->z, sv->mean, sv->rstd, w->ln_gamma, dropout_rate, dropout_key, dropout_seed_dev,
                           d_x, accumulate_dx, sc->d_z, gw ? gw->ln_gamma : nullptr, gw ? gw->ln_beta : nullptr, gw ? gw->b2 : nullptr, 1, s));
     Branches br(s);
-    if (gw) TRY(launch_gemm(D, D, M, sv->h, D, true, sc->d_z, D, false, nullptr, 0, nullptr, 1, 0, gw->w2, D, br.fork(0)));
     // d_h = (d_z W2^T) masked by relu'(h); its column sums are DenseRelu's bias gradient (epilogue)
     GroupedGemm g;
     g.M = M; g.N = D; g.K = D; g.TB = true; g.lda = g.ldb = g.ldc = D; g.round_out = 1; g.relu_mask = sv->h;
     g.A[0] = sc->d_z; g.B[0] = w->w2; g.C[0] = sc->d_h; g.colsum[0] = gw ? gw->b1 : nullptr;
     TRY(launch_gemm_umma_grouped(g, s));
-    if (gw) TRY(launch_gemm(D, D, M, x, D, true, sc->d_h, D, false, nullptr, 0, nullptr, 1, 0, gw->w1, D, br.fork(1)));
+    if (gw) {
+        // both weight gradients in ONE grouped split-K launch on a side chain: gW2 += h^T d_z, gW1 += x^T d_h
+        GroupedGemm wg;
+        wg.M = D; wg.N = D; wg.K = M; wg.groups = 2; wg.TA = true; wg.lda = wg.ldb = wg.ldc = D; wg.beta = 1;
+        wg.A[0] = sv->h; wg.B[0] = sc->d_z; wg.C[0] = gw->w2;
+        wg.A[1] = x; wg.B[1] = sc->d_h; wg.C[1] = gw->w1;
+        TRY(launch_gemm_umma_grouped(wg, br.fork(0)));
+    }
     TRY(launch_gemm(M, D, D, sc->d_h, D, false, w->w1, D, true, nullptr, 0, nullptr, 1, 0, d_x, D, s));
     return br.join_deferrable();
 }
