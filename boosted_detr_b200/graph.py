@@ -83,11 +83,18 @@ class GraphedTrainStep:
             else:
                 m._h2d(k, x, dtype, dst=dst)
 
-    def replay(self):
+    def _pre(self):
+        """The per-step device words the captured kernels read (learning rate, dropout seed), queued on the current stream."""
         m = self.model
         if self.optimizer_in_graph:
             m.optimizer.pre_replay()
-        m.push_dropout_seed()                     # this step's dropout seed -> the device word the captured kernels read
+        m.push_dropout_seed()
+
+    def replay(self):
+        m = self.model
+        if not getattr(self, "_primed", False):   # (already queued behind the previous launch by __call__(prefetch=...))
+            self._pre()
+        self._primed = False
         self.graph.replay()
         if m.grad_allreduce is not None and m.grad_bucket_hook is None:
             m.grad_allreduce(m._flat[1])          # non-overlapped mode: one all-reduce after the graph
@@ -96,7 +103,7 @@ class GraphedTrainStep:
         m.step_count += 1
         m.advance_dropout_seed()
 
-    # -- input prefetch (opt-in; NOT yet validated on the GPU: see DESIGN.md §7) -------------------------------------
+    # -- input prefetch ---------------------------------------------------------------------------------------------
     def prefetch(self, inputs):
         """Starts the H2D copy of the NEXT batch into a second set of device buffers on a copy stream, so that it runs
         underneath the step that is executing; `__call__(inputs)` with the same object then only does device-to-device
@@ -128,15 +135,26 @@ class GraphedTrainStep:
         self._staged_for = None
 
     def __call__(self, inputs, return_host=True, prefetch=None):
-        """One training step on `inputs`.  `prefetch` = the batch of the FOLLOWING step (optional): its H2D copy is
-        queued right behind this step's launch and overlaps with it."""
-        if getattr(self, "_staged_for", None) is inputs and inputs is not None:
+        """One training step on `inputs`.  `prefetch` = the batch of the FOLLOWING step (optional): its H2D copy runs on a
+        copy stream underneath this step, and everything else the next launch needs -- the staging -> static input copies
+        and the next step's learning-rate / dropout-seed words -- is queued on the main stream right BEHIND this step's
+        graph while the host would otherwise sit in the logs' synchronisation.  The next call then only launches the graph
+        (the host-side issue of ~8 small copies, ~50 us, no longer sits between two steps)."""
+        if getattr(self, "_primed_for", None) is inputs and inputs is not None:
+            pass                                  # inputs and per-step words are already in place
+        elif getattr(self, "_staged_for", None) is inputs and inputs is not None:
             self._take_prefetched()
         else:
             self.load(inputs)
+        self._primed_for = None
         self.replay()
         if prefetch is not None:
             self.prefetch(prefetch)
+            if self.optimizer_in_graph or self.model.optimizer is None:
+                # stream order keeps this behind the running graph, which still reads the current batch and words
+                self._take_prefetched()
+                self._pre()
+                self._primed, self._primed_for = True, prefetch
         if not return_host:
             return self.metrics
         return self.model.host_logs()

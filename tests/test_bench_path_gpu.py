@@ -115,6 +115,61 @@ def test_graph_replay_equals_eager_and_draws_fresh_masks(tc_mode):
         assert ge < 1e-4                                # float atomics (split-K reduce-adds, column sums) in a different order
 
 
+@pytest.mark.parametrize("lr0", [0.0, 0.05])
+def test_prefetched_call_equals_plain_call(tc_mode, lr0):
+    """The e2e path of bench.py: `gs(batch, prefetch=next_batch)` copies the next batch under the running step and queues
+    its staging -> static copies and the next step's learning-rate / dropout-seed words BEHIND the running graph.  Three
+    steps on three different pinned host batches, optimizer inside the graph, against three plain `gs(batch)` calls:
+      lr0 = 0     the weights never move, so every step's logs must be BIT-identical (right batch, right dropout seed per step);
+      lr0 = .05   a rate that changes every step: step 0 bit-identical, and after every call the device words hold exactly
+                  the values the schedule prescribes (the primed path has already pushed the NEXT step's rate and seed).
+                  Later logs are not compared: float-atomic noise in the weight gradients flips near-tied assignments."""
+    from boosted_detr_b200.graph import GraphedTrainStep
+    from boosted_detr_b200.optimizers import SGD, CosineDecayRestarts
+    from util import synth_targets
+
+    def batches(model, n):
+        out = []
+        for i in range(n):
+            rng = np.random.default_rng(100 + i)
+            cat, attr, box, num = synth_targets(rng, 4, 20, model.num_categories, model.num_attributes, attr_p=0.05)
+            feats = np.tanh(rng.standard_normal((4, 20, 20, 256))).astype(np.float32)
+            d = {"features": feats, "category": cat, "attribute": attr, "bbox": box, "num_objects": num.astype(np.int32)}
+            out.append({k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in d.items()})
+        return out
+
+    results = []
+    for use_prefetch in (False, True):
+        model, w, inputs = _model_and_data(N=2, B=4, rows=20, cols=20)
+        lr = CosineDecayRestarts(initial_learning_rate=lr0, first_decay_steps=2, m_mul=.95, alpha=0.1)
+        model.compile(optimizer=SGD(learning_rate=lr, momentum=.9, nesterov=True, clipnorm=0.1))
+        w0 = _snapshot(model)
+        bs = batches(model, 3)
+        model.dropout_seed = 5
+        gs = GraphedTrainStep(model, bs[0])
+        model.set_weights_dict(w0)
+        it0, seed0 = model.optimizer.iterations, 4242
+        model.dropout_seed = seed0
+        logs, words = [], []
+        for i, b in enumerate(bs):
+            nxt = bs[i + 1] if (use_prefetch and i + 1 < len(bs)) else None
+            logs.append(gs(b, prefetch=nxt))
+            torch.cuda.synchronize()
+            ahead = 1 if nxt is not None else 0            # the primed path has pushed the next step's words already
+            assert float(model.optimizer._lr_dev) == np.float32(lr(it0 + i + ahead)), (use_prefetch, i)
+            assert int(model._seed_dev) == seed0 + i + ahead, (use_prefetch, i)
+        assert model.optimizer.iterations == it0 + 3 and model.dropout_seed == seed0 + 3
+        results.append((logs, _snapshot(model)))
+    (l0, w_plain), (l1, w_pref) = results
+    assert l0[0] == l1[0], (l0[0], l1[0])                # same weights, same batch, same seed: bit-identical forward
+    assert l0[0] != l0[1]                                # different batches really give different logs
+    if lr0 == 0.0:
+        assert l0 == l1, (l0, l1)
+        worst = max(nerr(w_pref[k], w_plain[k]) for k in w_plain)
+        print(f"prefetched path vs plain calls, 3 steps at lr 0: logs bit-identical, worst weight / statistic difference {worst:.2e}")
+        assert worst < 1e-6
+
+
 def test_concurrency_switch_does_not_change_results(tc_mode):
     """bdetr_set_concurrency(0/1) only changes which streams the kernels run on."""
     from boosted_detr_b200 import _lib
