@@ -22,7 +22,7 @@ heads = (SingleClassPredictionHead(82, D, Q, name="c"), MultiClassPredictionHead
 dec = torch.randn(B, Q, D, device="cuda")
 rng = np.random.default_rng(0)
 sets = {}
-for (C, A) in ((82, 3), (48, 296)):
+for (C, A) in ((48, 296), (82, 3)):       # (82, 3) last: the assignment below solves ITS cost matrix
     Bm, T, Qm = 256, 100, 300
     tr = synth_targets(rng, Bm, T, C, A); pr = synth_preds(rng, Bm, Qm, C, A)
     sets[(C, A)] = [torch.from_numpy(np.ascontiguousarray(v)).cuda() for v in (*tr, *pr)]
