@@ -128,22 +128,38 @@ class BoostedDETR:
             m = re.match(r"[A-Za-z]+_(\d+)/", name)
             return int(m.group(1)) if m else 0                # DecoderPrep (shared queries): final only after block 0
 
+        def part_of(name):
+            # inside a block: decoder / heads variables first (their gradients are final long before the encoder's: the
+            # decoder-side chains run ahead), encoder variables -- and the shared queries, final only at the very end --
+            # last, so a block's bucket splits into two contiguous sub-ranges that can be all-reduced separately
+            return 1 if name.startswith(("ImageEncoderAttention_", "DecoderPrep")) else 0
+
         named = [(n, o, k) for n, o, k in self.named_weights() if k not in o._non_trainable]
-        named.sort(key=lambda nok: -block_of(nok[0]))         # stable: keeps the layer order inside a block
+        named.sort(key=lambda nok: (-block_of(nok[0]), part_of(nok[0])))      # stable: keeps the layer order inside a part
         self._index, off = {}, 0
         self._buckets, cur, start = [], None, 0
+        self._split = {}                                      # block -> first float of its encoder part
         for n, o, k in named:
             blk = block_of(n)
             if cur is None:
                 cur = blk
             if blk != cur:
                 self._buckets.append((cur, start, off))
+                self._split.setdefault(cur, off)
                 cur, start = blk, off
+            if part_of(n) == 1:
+                self._split.setdefault(blk, off)
             w = o._weights[k]
             self._index[n] = (off, w.numel(), tuple(w.shape))
             off += (w.numel() + 3) // 4 * 4               # keep every tensor 16-byte aligned
         self._buckets.append((cur, start, off))
+        self._split.setdefault(cur, off)
         assert [b for b, _, _ in self._buckets] == list(range(N - 1, -1, -1)), self._buckets
+        # the ranges the bucket pipeline works on (all-reduce + optimizer update each): decoder part, encoder part per block
+        self._ranges = []
+        for b, lo, hi in self._buckets:
+            mid = self._split[b]
+            self._ranges += [r for r in ((lo, mid), (mid, hi)) if r[1] > r[0]]
         flat_w, flat_g, flat_tc = zeros(off), zeros(off), zeros(off)
         for n, o, k in named:
             o0, cnt, shp = self._index[n]
@@ -607,6 +623,12 @@ class BoostedDETR:
                 decoder_side(i - 1)          # enqueued before encoder i: encoder i accumulates its input gradient into d_enc[i-1]
             main.wait_event(evs[i])
             self._mark(f"bwd enc{i} may start (main)")
+            if self.grad_bucket_hook is not None and self._flat is not None:
+                # decoder / heads variables of block i are final once the decoder-side chain (grad_evs) and the hoisted
+                # self-attention (self_evs) have passed: that sub-range goes out while encoder i's backward runs
+                _, lo, hi = self._buckets[N - 1 - i]
+                if self._split[i] > lo:
+                    self.grad_bucket_hook(i, lo, self._split[i], [self_evs[i], grad_evs[i]])
             enc = self.EncoderTransformerBlocks[i]
             d_out = d_encs[i]                # gradient of encoder i's output: decoder i's k/v paths (+ encoder i+1, accumulated)
             if d_out is not None and (enc.trainable or (i > 0 and below[i - 1]) or (i == 0 and neck_tr)):
@@ -628,8 +650,10 @@ class BoostedDETR:
                 if i == 0:
                     hook_evs = [e for e in self_evs if e is not None] + [grad_evs[0]]
                 # encoder i's parameter-gradient chains are joined INTO the consumer's stream (bucket pipeline), not into
-                # this one: the encoder chain keeps running
-                self.grad_bucket_hook(i, lo, hi, hook_evs, join_from=torch.cuda.current_stream())
+                # this one: the encoder chain keeps running.  Only the encoder part of the bucket is left (its positional
+                # table also collects decoder i's key-path gradient; block 0's part holds the shared queries).
+                if hi > self._split[i]:
+                    self.grad_bucket_hook(i, self._split[i], hi, hook_evs, join_from=torch.cuda.current_stream())
         _lib.call("bdetr_join", stream_ptr())
         for bs in bstreams:
             main.wait_stream(bs)

@@ -18,7 +18,8 @@ import torch
 from . import _lib
 from .device import ptr, stream_ptr, zeros
 
-CHUNK = 16384
+CHUNK = 2048        # floats per CTA of the update kernels: a 256 x 256 kernel is 32 CTAs (16 K-element chunks left a 0.5 M-float
+                    # range on ~50 CTAs: 24 us alone, 40-70 us beside the backward, all on the bucket pipeline's critical tail)
 
 
 class CosineDecayRestarts:
@@ -116,8 +117,8 @@ class SGD:
 
     # -- per-bucket form: the update of boosted block i's variables right behind its gradient all-reduce -------------
     def _ensure_bucket_tables(self, model):
-        """One chunk table per gradient bucket (model._buckets: contiguous ranges of the flat buffers, one per boosted
-        block in backward order), so the clip + update of a block can be queued as soon as its gradients are final
+        """One chunk table per gradient range (model._ranges: contiguous ranges of the flat buffers -- the decoder / heads
+        part and the encoder part of every boosted block, in backward order), so the clip + update of a range can be queued as soon as its gradients are final
         (the optimizer step fused behind the all-reduce epilogue) instead of after the whole backward."""
         from .layers import Layer
         self._ensure_table(model)
@@ -126,7 +127,9 @@ class SGD:
             return
         slots = self.trainable_slots(model)
         tabs, counts = [], []
-        for _, lo, hi in model._buckets:
+        ranges = list(getattr(model, "_ranges", None) or [(lo, hi) for _, lo, hi in model._buckets])
+        self._brange = {r: k for k, r in enumerate(ranges)}      # (first float, one-past-last float) -> table index
+        for lo, hi in ranges:
             t = self.chunk_table([sl for sl in slots if lo <= sl[1] < hi])
             tabs.append(t)
             counts.append(len(t))
@@ -138,8 +141,10 @@ class SGD:
         self._bfirst = [int(x) for x in np.concatenate([[0], np.cumsum(counts)[:-1]])]
         self._btab_key = key
 
-    def launch_bucket(self, model, bucket_index, lr=0.0, lr_dev=None):
-        """Clip + update of the variables of gradient bucket `bucket_index` on the current stream."""
+    def launch_bucket(self, model, lo_hi, lr=0.0, lr_dev=None):
+        """Clip + update of the variables in the gradient range `lo_hi` = (first float, one-past-last float), one of
+        model._ranges, on the current stream."""
+        bucket_index = self._brange[tuple(lo_hi)]
         n, first = self._bcounts[bucket_index], self._bfirst[bucket_index]
         if n == 0:
             return

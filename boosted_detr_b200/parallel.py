@@ -117,9 +117,10 @@ class DataParallel:
     sum over replicas of d(loss_replica / world)/d(theta).
 
     overlap=True (default): the flat gradient buffer is laid out block by block in backward order
-    (BoostedDETR._flatten), and as soon as the backward has finished boosted block i its bucket (~5 MB) is
-    all-reduced on a communication stream underneath the backward of blocks i-1 .. 0; only the last bucket is
-    exposed.  The collectives are issued in the same order on every rank and are captured into the CUDA graph of
+    (BoostedDETR._flatten), and the bucket of boosted block i (~5 MB) goes out in two pieces on a communication stream:
+    its decoder / heads part (~3.8 MB) as soon as the decoder-side chain of block i is done -- under encoder i's backward
+    -- and its encoder part (~1.6 MB) when encoder i is done, under the backward of blocks i-1 .. 0; only block 0's
+    encoder part is exposed.  The collectives are issued in the same order on every rank and are captured into the CUDA graph of
     the step together with the kernels.  overlap=False: one all-reduce of the whole buffer after the backward."""
 
     def __init__(self, model, overlap=True, bucket_optimizer=True):
@@ -147,6 +148,11 @@ class DataParallel:
             self.comm_stream = torch.cuda.Stream()
         return self.comm_stream
 
+    def _opt(self):
+        if getattr(self, "opt_stream", None) is None:
+            self.opt_stream = torch.cuda.Stream()
+        return self.opt_stream
+
     def reduce_bucket(self, block: int, lo: int, hi: int, events=(), join_from=None):
         """All-reduce flat_grads[lo:hi] (boosted block `block`) on the communication stream, ordered after the
         caller's stream and `events`."""
@@ -159,18 +165,27 @@ class DataParallel:
             from . import _lib
             _lib.call("bdetr_join_into", ctypes.c_void_p(join_from.cuda_stream), ctypes.c_void_p(comm.cuda_stream))
         with torch.cuda.stream(comm):
+            self.model._mark(f"block {block} range [{lo}:{hi}) final (comm)")
             if self.world > 1:
                 allreduce_gradients(self.model._flat[1][lo:hi])
-            # clip + SGD update of this block's variables right behind its all-reduce
-            if self.opt_lr is not None:
-                m = self.model
-                bi = next(k for k, (b, _, _) in enumerate(m._buckets) if b == block)
-                m.optimizer.launch_bucket(m, bi, self.opt_lr[0], self.opt_lr[1])
+                self.model._mark(f"block {block} range all-reduced (comm)")
+        # clip + SGD update of this range's variables right behind its all-reduce -- on a stream of its
+        # own, so the NEXT range's all-reduce does not queue behind this update (the communication stream was a serial
+        # chain of all-reduce + update pairs that outlasted the backward: tools/trace_step.py under torchrun)
+        if self.opt_lr is not None:
+            m = self.model
+            opt = self._opt() if self.world > 1 else comm
+            opt.wait_stream(comm)
+            with torch.cuda.stream(opt):
+                m.optimizer.launch_bucket(m, (lo, hi), self.opt_lr[0], self.opt_lr[1])
+                m._mark(f"block {block} range updated (opt)")
 
     def finish(self, flat_grads: torch.Tensor):
         """Called at the end of the backward: joins the bucketed all-reduces, or does the single one."""
         if self.overlap:
             torch.cuda.current_stream().wait_stream(self._comm())
+            if getattr(self, "opt_stream", None) is not None:
+                torch.cuda.current_stream().wait_stream(self.opt_stream)
         elif self.world > 1:
             allreduce_gradients(flat_grads)
 
