@@ -387,6 +387,8 @@ int launch_attention_bwd_umma(int B, int H, int Lq, int Lk, int d, const float *
         BDETR_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dkv));
         optin = true;
     }
+    // (dQ and dK/dV back to back on one stream: running them side by side -- delta from a kernel of its own -- was measured
+    // and dropped, 2.55 -> 2.69 ms per step: two 512-CTA kernels at once thrash the SM slots the backward is bound by)
     dim3 gq(ceil_div(Lq, FB_ROWS), H, B);
     launch_k(attention_bwd_dq_umma_kernel, gq, FB_THREADS, smem_dq, s, q128, do128, k64, v64, k64mn, H, Lq, Lk, o, d_o, lse, delta, d_qp,
                                                                 scale, scale_log2, round_out);
