@@ -209,7 +209,8 @@ def _attn_forward_fused(self, query, memory, fold, training=False, dropout_key=0
     rate = self.rate if training else 0.0
     w, _ = self._structs()
     lib = _lib.load()
-    if lib.bdetr_get_mode() == _lib.MODE_FP16:          # fp16 copies of q / k / v for the long-sequence attention kernel
+    if lib.bdetr_get_mode() == _lib.MODE_FP16 and not training:      # fp16 copies of q / k / v for the long-sequence attention kernel (inference
+        # forward only: the backward kernels recompute S from the TF32 operands, and that mixed pairing is not tested)
         n16 = lib.bdetr_attention_f16_workspace_bytes(B, H, Lq, Lk, D // H)
         if n16:
             sv["ws16"] = torch.empty(n16 // 2, dtype=torch.float16, device=query.device)

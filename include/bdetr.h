@@ -42,7 +42,8 @@ typedef enum {
                            * sequences: the config-5 encoder self-attention): q / k / v and the softmax weights P are fp16
                            * (tcgen05.mma kind::f16), accumulation fp32 -- the reference's Keras `mixed_float16` policy
                            * (parameters.py:73).  Needs bdetr_attn_saved.ws16 / the *_f16 entry point's workspace; shapes the
-                           * fp16 kernel does not serve, and every backward, run exactly as in BDETR_MODE_TF32. */
+                           * fp16 kernel does not serve, and every backward, run exactly as in BDETR_MODE_TF32 (the Python
+                           * layers hand ws16 over for inference forwards only). */
 
 int bdetr_version(void);
 const char *bdetr_last_error(void);
