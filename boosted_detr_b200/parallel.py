@@ -117,10 +117,11 @@ class DataParallel:
     sum over replicas of d(loss_replica / world)/d(theta).
 
     overlap=True (default): the flat gradient buffer is laid out block by block in backward order
-    (BoostedDETR._flatten), and the bucket of boosted block i (~5 MB) goes out in two pieces on a communication stream:
-    its decoder / heads part (~3.8 MB) as soon as the decoder-side chain of block i is done -- under encoder i's backward
-    -- and its encoder part (~1.6 MB) when encoder i is done, under the backward of blocks i-1 .. 0; only block 0's
-    encoder part is exposed.  The collectives are issued in the same order on every rank and are captured into the CUDA graph of
+    (BoostedDETR._flatten), and as soon as the backward has finished boosted block i its bucket (~5 MB) is
+    all-reduced on a communication stream underneath the backward of blocks i-1 .. 0; only the last bucket is
+    exposed (BDETR_SPLIT_RANGES=1 sends the decoder / heads part of a bucket ahead of its encoder part: no gain measured).
+    The clip + SGD update of a bucket follows its all-reduce on a third stream, so the next all-reduce never waits for it.
+    The collectives are issued in the same order on every rank and are captured into the CUDA graph of
     the step together with the kernels.  overlap=False: one all-reduce of the whole buffer after the backward."""
 
     def __init__(self, model, overlap=True, bucket_optimizer=True):
