@@ -10,6 +10,7 @@ chunk table, so they are neither clipped nor updated).  The update itself is bde
 from __future__ import annotations
 
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -18,8 +19,8 @@ import torch
 from . import _lib
 from .device import ptr, stream_ptr, zeros
 
-CHUNK = 2048        # floats per CTA of the update kernels: a 256 x 256 kernel is 32 CTAs (16 K-element chunks left a 0.5 M-float
-                    # range on ~50 CTAs: 24 us alone, 40-70 us beside the backward, all on the bucket pipeline's critical tail)
+CHUNK = int(os.environ.get("BDETR_OPT_CHUNK", "2048"))    # floats per CTA of the update kernels: a 256 x 256 kernel is 32 CTAs (16 K-element
+                    # chunks left a 0.5 M-float range on ~50 CTAs: 24 us alone, 40-70 us beside the backward, all on the bucket pipeline's critical tail)
 
 
 class CosineDecayRestarts:
