@@ -41,3 +41,22 @@ def test_no_oracle_import_in_product():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("the oracle", ""), f"{f} must not reference oracle/"
+
+
+def test_host_side_queries_need_no_gpu():
+    """Size / mode queries are host logic: they must answer on a GPU-less build host (no kernel is launched)."""
+    from boosted_detr_b200 import _lib
+    lib = _lib.load()
+    # fp16 attention workspace: q16 | k16 | v16 halves for shapes the long-sequence kernel serves, 0 otherwise
+    assert lib.bdetr_attention_f16_workspace_bytes(4, 8, 20020, 20020, 32) == 2 * 3 * 4 * 20020 * 256
+    assert lib.bdetr_attention_f16_workspace_bytes(16, 8, 400, 400, 32) == 0          # config 2 keeps the TF32 kernels
+    assert lib.bdetr_attention_f16_workspace_bytes(4, 8, 20020, 20020, 64) == 0          # head dim must be 32
+    assert lib.bdetr_attention_f16_workspace_bytes(0, 8, 20020, 20020, 32) == 0
+    # the three compute modes round-trip through set / get; BDETR_MODE_FP16 is the tensor-core mode plus the operand switch
+    try:
+        for mode in (_lib.MODE_TF32, _lib.MODE_FP16, _lib.MODE_FP32):
+            assert lib.bdetr_set_mode(mode) == 0 and lib.bdetr_get_mode() == mode
+            assert _lib.tc_mode() == (mode != _lib.MODE_FP32)
+    finally:
+        lib.bdetr_set_mode(_lib.MODE_FP32)
+    assert lib.bdetr_cost_targets_bytes(256, 100, 82, 3) > 0 and lib.bdetr_cost_targets_bytes(0, 100, 82, 3) == 0
