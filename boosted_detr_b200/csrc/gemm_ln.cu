@@ -521,8 +521,8 @@ gemm_ln_split_kernel(const __grid_constant__ LnSplitMaps maps, const __grid_cons
     if (store_rows && elect_one()) {
         tma_store_2d(&maps.out, smem + (size_t)(g * 4 + q) * 4096, n0 + g * 32, m0 + q * 32);
         tma_store_commit();
-        tma_store_wait_read_all();
     }
+    tma_store_wait_read_all();                          // every lane: whichever lane committed the z / out groups waits for them
     __syncwarp();
     LNS_STAMP(5);
     tc_fence_before();
